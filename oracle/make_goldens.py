@@ -1,0 +1,129 @@
+"""Generate ``tests/golden/*.npz`` by running the UNMODIFIED reference (``/root/reference``) on small synthetic
+frustums.  TEST INFRASTRUCTURE ONLY; runs in the build container (the reference does not travel to the GPU box).
+
+    python -m oracle.make_goldens            # rewrites every fixture
+
+Each fixture stores all inputs (images, intrinsics, poses, encoder features, MLP weights, rays, jitter ``u``), the
+configuration (JSON) and the reference outputs of ``_RenderWrapper.forward`` (models/common/render/nerf.py:19-45) with
+every optional output requested, plus ``BTSNet.forward`` point-query outputs (models/bts/model/models_bts.py:266-338).
+The jitter is injected by seeding torch right before the reference's ``torch.rand_like`` (nerf.py:116): on CPU
+``rand_like`` of a (B,K) tensor consumes the same stream as ``torch.rand((B,K))`` (checked below, bit-exact z).
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from behindthescenes_b200 import synthetic as syn  # noqa: E402
+from oracle import ref_import  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def fixtures():
+    P = syn._pose
+    out = []
+    out.append(syn.cfg2_kitti360_eval(H=16, W=48, K=64, stereo=True, learn_empty=True, lin_out_bias=0.0, seed=1,
+                                      ray_subsample=192))
+    out[-1].name = "cfg2_small_bias0"
+    out.append(syn.cfg2_kitti360_eval(H=16, W=48, K=64, stereo=True, learn_empty=True, lin_out_bias=-4.0, seed=2,
+                                      ray_subsample=192))
+    out[-1].name = "cfg2_small_bias4"
+    out.append(syn.cfg2_kitti360_eval(H=16, W=48, K=32, stereo=False, learn_empty=True, lin_out_bias=-4.0, seed=3,
+                                      ray_subsample=192))
+    out[-1].name = "cfg1_small_K32"
+    out.append(syn.cfg3_kitti_raw_train(H=20, W=64, K=64, n=2, seed=4, lin_out_bias=-4.0, ray_subsample=96))
+    out[-1].name = "cfg3_small_n2"
+    out.append(syn.cfg4_re10k_nvs(H=24, W=36, K=128, seed=5, lin_out_bias=-4.0, ray_subsample=96))
+    out[-1].name = "cfg4_small"
+    # edge cases: linear depth sampling, linear depth code, white background, no alpha cap, rays that leave the
+    # frustum and pass behind the encoder camera (clamped z -> huge |uv|), K=32, learn_empty on
+    mc = syn.kitti_model_conf(learn_empty=True, z_near=0.5, z_far=20.0, inv_z=False)
+    rc = syn.kitti_renderer_conf(32, lindisp=False, hard_alpha_cap=False, white_bkgd=True)
+    out.append(syn.make_workload("edge_linear_white", H=16, W=48, poses=[P(), P(tx=0.3, yaw_deg=8.0)], model_conf=mc,
+                                 renderer_conf=rc, ids_encoder=[0], ids_render=[0, 1],
+                                 ray_poses=[P(tx=1.0, tz=4.0, yaw_deg=160.0), P(ty=-0.5, tz=-2.0, yaw_deg=-35.0, pitch_deg=10.0)],
+                                 ray_subsample=192, seed=6, lin_out_bias=-2.0))
+    # distance code with inverse depth and learn_empty, 1 block, Hd=64
+    mc = syn.kitti_model_conf(learn_empty=True, n_blocks=1, code_mode="distance")
+    rc = syn.kitti_renderer_conf(64)
+    out.append(syn.make_workload("dist_block1", H=16, W=48, poses=[P(), P(tx=0.54)], model_conf=mc, renderer_conf=rc,
+                                 ids_encoder=[0], ids_render=[1], ray_poses=[P(tx=0.2, tz=-0.5, yaw_deg=12.0)],
+                                 ray_subsample=128, seed=7, lin_out_bias=-3.0))
+    return out
+
+
+def run_reference(ref, wl: syn.Workload):
+    torch.manual_seed(wl.weight_seed)
+    net = ref_import.make_reference_net(ref, wl.model_conf, wl.feats)
+    g = torch.Generator().manual_seed(wl.weight_seed + 100)
+    with torch.no_grad():
+        net.mlp_coarse.lin_out.bias.fill_(wl.lin_out_bias)
+        for blk in net.mlp_coarse.blocks:   # reference zero-inits fc_1 (resnetfc.py:40): randomise to exercise it
+            blk.fc_1.weight.copy_(torch.randn(blk.fc_1.weight.shape, generator=g) * (2.0 / blk.fc_1.weight.shape[1]) ** 0.5 * 0.5)
+            blk.fc_0.bias.copy_(torch.randn(blk.fc_0.bias.shape, generator=g) * 0.1)
+            blk.fc_1.bias.copy_(torch.randn(blk.fc_1.bias.shape, generator=g) * 0.1)
+        net.mlp_coarse.lin_in.bias.copy_(torch.randn(net.mlp_coarse.lin_in.bias.shape, generator=g) * 0.1)
+    renderer = ref.NeRFRenderer.from_conf(wl.renderer_conf)
+    wrapped = renderer.bind_parallel(net, gpus=None).eval()
+    with torch.no_grad():
+        net.encode(wl.images, wl.Ks, wl.poses_c2w, ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
+        net.set_scale(0)
+        # inject u: reseed so that rand_like (nerf.py:116) reproduces wl.u
+        B, K = wl.u.shape
+        torch.manual_seed(12345)
+        u_check = torch.rand((B, K))
+        torch.manual_seed(12345)
+        out = wrapped(wl.rays, want_weights=True, want_alphas=True, want_z_samps=True, want_rgb_samps=True)
+        coarse = out["coarse"]
+        # point query on the first ray points + a few hand-placed points (behind camera, on the optical axis)
+        z = coarse["z_samps"]
+        pts = (wl.rays[:, :, None, :3] + z.unsqueeze(-1) * wl.rays[:, :, None, 3:6])[:, ::7].reshape(wl.rays.shape[0], -1, 3)
+        extra = torch.tensor([[0.0, 0.0, -1.0], [0.0, 0.0, 5.0], [100.0, 0.0, 1.0], [0.0, 0.0, 1e-4]]).view(1, -1, 3)
+        pts = torch.cat((pts[:, :500], extra.expand(pts.shape[0], -1, -1)), 1).contiguous()
+        q_rgb, q_inv, q_sig = net(pts)
+        d_rgb, d_inv, d_sig = net(pts, only_density=True)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items() if not k.startswith("encoder.")}
+    return u_check, coarse, sd, dict(pts=pts, q_rgb=q_rgb, q_invalid=q_inv, q_sigma=q_sig, d_rgb=d_rgb,
+                                     d_invalid=d_inv, d_sigma=d_sig)
+
+
+def main():
+    ref = ref_import.load_reference()
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    for wl in fixtures():
+        u, coarse, sd, q = run_reference(ref, wl)
+        # the stratified depths the reference produced must be reproducible from u (bit-exact)
+        from oracle import bts_oracle as orc
+        z_from_u = orc.stratified_depths(wl.rays.reshape(-1, 8), wl.renderer_conf["n_coarse"], wl.renderer_conf["lindisp"], u)
+        assert torch.equal(z_from_u.view_as(coarse["z_samps"]), coarse["z_samps"]), "jitter injection is not bit-exact"
+        arrays = {
+            "images": wl.images, "Ks": wl.Ks, "poses_c2w": wl.poses_c2w, "feats": wl.feats, "rays": wl.rays, "u": u,
+        }
+        for k, v in sd.items():
+            arrays["sd/" + k] = v
+        for k, v in coarse.items():
+            arrays["out/" + k] = v
+        for k, v in q.items():
+            arrays["query/" + k] = v
+        meta = {"name": wl.name, "model_conf": wl.model_conf, "renderer_conf": wl.renderer_conf,
+                "ids_encoder": wl.ids_encoder, "ids_render": wl.ids_render,
+                "reference": "Brummi/BehindTheScenes @ /root/reference (unmodified; stubs: dotmap, lpips, omegaconf; "
+                             "encoder replaced by a feature stand-in)", "torch": torch.__version__}
+        path = os.path.join(GOLDEN_DIR, wl.name + ".npz")
+        np.savez_compressed(path, meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8),
+                            **{k: v.detach().cpu().numpy() for k, v in arrays.items()})
+        inv = coarse["invalid"]
+        print(f"{wl.name}: rays {tuple(wl.rays.shape)} K={wl.renderer_conf['n_coarse']} depth "
+              f"[{coarse['depth'].min():.2f},{coarse['depth'].max():.2f}] invalid frac {inv.mean():.3f} "
+              f"-> {os.path.getsize(path) / 1e3:.0f} kB")
+
+
+if __name__ == "__main__":
+    main()
