@@ -1,0 +1,94 @@
+"""ctypes binding of the C ABI in ``include/bts_b200.h`` (libbts_b200.so).
+
+There is no CPU implementation behind this module: if the CUDA library is missing or fails to load, importing the
+render path raises -- by design (BASELINE.json north_star: "no CPU fallback").
+"""
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libbts_b200.so")
+
+BTS_MAX_BLOCKS = 8
+ABI_VERSION = 1
+_fp = C.POINTER(C.c_float)
+
+
+class BtsScene(C.Structure):
+    _fields_ = [("n", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Hd", C.c_int32),
+                ("G", C.c_void_p), ("g_empty", C.c_void_p), ("K_f", C.c_void_p), ("w2c_f", C.c_void_p),
+                ("Vc", C.c_int32), ("Cc", C.c_int32), ("Hc", C.c_int32), ("Wc", C.c_int32),
+                ("img4", C.c_void_p), ("K_c", C.c_void_p), ("w2c_c", C.c_void_p)]
+
+
+class BtsMlp(C.Structure):
+    _fields_ = [("C", C.c_int32), ("P", C.c_int32), ("Hd", C.c_int32), ("n_blocks", C.c_int32),
+                ("w_in", C.c_void_p), ("b_in", C.c_void_p),
+                ("fc0_w", C.c_void_p * BTS_MAX_BLOCKS), ("fc0_b", C.c_void_p * BTS_MAX_BLOCKS),
+                ("fc1_w", C.c_void_p * BTS_MAX_BLOCKS), ("fc1_b", C.c_void_p * BTS_MAX_BLOCKS),
+                ("w_out", C.c_void_p), ("b_out", C.c_void_p)]
+
+
+class BtsRenderCfg(C.Structure):
+    _fields_ = [("n_coarse", C.c_int32), ("lindisp", C.c_int32), ("hard_alpha_cap", C.c_int32),
+                ("white_bkgd", C.c_int32), ("inv_z", C.c_int32), ("code_mode", C.c_int32),
+                ("learn_empty", C.c_int32), ("num_freqs", C.c_int32), ("include_input", C.c_int32),
+                ("freq_factor", C.c_float), ("z_near", C.c_float), ("z_far", C.c_float),
+                ("inv_z_far", C.c_float), ("inv_z_range", C.c_float), ("z_range", C.c_float),
+                ("z_steps", C.c_void_p), ("step", C.c_float), ("precision", C.c_int32)]
+
+
+class BtsRenderOut(C.Structure):
+    _fields_ = [("rgb", C.c_void_p), ("depth", C.c_void_p), ("invalid", C.c_void_p), ("weights", C.c_void_p),
+                ("alphas", C.c_void_p), ("z_samps", C.c_void_p), ("rgb_samps", C.c_void_p)]
+
+
+EXPORTS = {
+    "bts_abi_version": (C.c_int, []),
+    "bts_last_error": (C.c_char_p, []),
+    "bts_last_kernel": (C.c_char_p, []),
+    "bts_fold_features": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bts_pack_images": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "bts_render_fwd": (C.c_int, [C.POINTER(BtsScene), C.POINTER(BtsMlp), C.POINTER(BtsRenderCfg), C.c_void_p,
+                                 C.c_int64, C.c_int64, C.c_void_p, C.c_uint64, C.POINTER(BtsRenderOut), C.c_void_p]),
+    "bts_query_field": (C.c_int, [C.POINTER(BtsScene), C.POINTER(BtsMlp), C.POINTER(BtsRenderCfg), C.c_void_p,
+                                  C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+class BtsCudaError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libbts_b200.so (building nothing: see ``behindthescenes_b200.build``).  Raises if unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise BtsCudaError(f"{LIB_PATH} not found: build it with `python -m behindthescenes_b200.build` "
+                           "(there is no CPU fallback for the render path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)      # AttributeError if a declared symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    v = lib.bts_abi_version()
+    if v != ABI_VERSION:
+        raise BtsCudaError(f"libbts_b200.so ABI {v} != binding ABI {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc == 0:
+        return
+    msg = load().bts_last_error().decode(errors="replace")
+    if rc == -2:
+        raise NotImplementedError(f"{what}: {msg}")
+    if rc == -1:
+        raise ValueError(f"{what}: {msg}")
+    raise BtsCudaError(f"{what}: {msg}")

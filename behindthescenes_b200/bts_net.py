@@ -1,0 +1,276 @@
+"""Drop-in ``BTSNet`` whose field evaluation runs in the sm_100a CUDA library (host mirror of
+``models/bts/model/models_bts.py``).
+
+Same constructor config keys, attributes, ``encode`` cache (``grid_f_*`` / ``grid_c_*``), ``set_scale`` and
+``forward(xyz, coarse, viewdirs, far, only_density) -> (rgb, invalid, sigma)`` contract as the reference, and the same
+state-dict keys (``encoder.*``, ``code_xyz._freqs/_phases``, ``mlp_coarse.*``, ``empty_feature``).  ``sample_features``
+/ ``sample_colors`` + the MLP of the reference (``models_bts.py:138-338``) are replaced by
+``bts_query_field`` / ``bts_render_fwd`` (``include/bts_b200.h``); the ResNet encoder stays a stock torch module.
+
+There is NO torch/CPU implementation of the field here: without the CUDA library or on CPU tensors the calls raise.
+Configurations the CUDA path does not implement (``sample_color=False``, ``combine_ids``, several encoder views,
+``empty_empty``, ``use_viewdirs``) raise ``NotImplementedError`` instead of falling back (SURVEY.md §8b "Errors").
+"""
+import ctypes as C
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import _lib
+from .code import PositionalEncoding
+from .resnetfc import make_mlp
+
+EPS = 1e-3
+
+
+def _reference_backbone(conf):
+    """The encoder is out of the hot path (BASELINE.json north_star: "the ResNet encoder remains a stock torch
+    module"): when this class is dropped into the reference tree its own factory builds it."""
+    try:
+        from models.common.backbones.backbone_util import make_backbone  # the reference package, if on sys.path
+    except Exception as e:  # pragma: no cover - depends on deployment
+        raise RuntimeError("BTSNet needs an encoder: pass `encoder=` or run inside the reference tree so that "
+                           "models.common.backbones.backbone_util.make_backbone is importable") from e
+    return make_backbone(conf)
+
+
+def _dev_f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.contiguous().float()
+    return t
+
+
+class BTSNet(nn.Module):
+    def __init__(self, conf, encoder: nn.Module = None):
+        super().__init__()
+        self.d_min = conf.get("z_near")
+        self.d_max = conf.get("z_far")
+        self.learn_empty = conf.get("learn_empty", True)
+        self.empty_empty = conf.get("empty_empty", False)
+        self.inv_z = conf.get("inv_z", True)
+        self.color_interpolation = conf.get("color_interpolation", "bilinear")
+        self.code_mode = conf.get("code_mode", "z")
+        if self.code_mode not in ("z", "distance"):
+            raise NotImplementedError(f"Unknown mode for positional encoding: {self.code_mode}")
+        self.flip_augmentation = conf.get("flip_augmentation", False)
+        self.return_sample_depth = conf.get("return_sample_depth", False)
+        self.sample_color = conf.get("sample_color", True)
+        if not self.sample_color or self.empty_empty or self.return_sample_depth or self.color_interpolation != "bilinear":
+            raise NotImplementedError("B200 render path implements sample_color=True, empty_empty=False, "
+                                      "return_sample_depth=False, bilinear colours (all shipped configs)")
+
+        self.encoder = encoder if encoder is not None else _reference_backbone(conf["encoder"])
+        self.code_xyz = PositionalEncoding.from_conf(conf["code"], d_in=3)
+        d_in = self.encoder.latent_size + self.code_xyz.d_out
+        self._d_in, self._d_out = d_in, 1
+        self.mlp_coarse = make_mlp(conf["mlp_coarse"], d_in, d_out=1)
+        self.mlp_fine = make_mlp(conf["mlp_fine"], d_in, d_out=1, allow_empty=True)
+        if self.learn_empty:
+            self.empty_feature = nn.Parameter(torch.randn((self.encoder.latent_size,), requires_grad=True))
+        self._scale = 0
+        self._encode_gen = 0
+        self._scene_cache = {}
+        self.grid_f_features = None
+
+    # ------------------------------------------------------------------ reference API
+    def set_scale(self, scale):
+        self._scale = scale
+
+    def get_scale(self):
+        return self._scale
+
+    def compute_grid_transforms(self, *args, **kwargs):
+        pass
+
+    def encode(self, images, Ks, poses_c2w, ids_encoder=None, ids_render=None, images_alt=None, combine_ids=None):
+        """Boundary producer, kept in torch (models_bts.py:65-136): selects views, runs the encoder once, caches the
+        feature maps / cameras / colour images the render kernels read."""
+        if combine_ids is not None:
+            raise NotImplementedError("combine_ids (view groups) is not implemented on the B200 render path")
+        w2c = torch.inverse(poses_c2w)
+        v = images.shape[1]
+        ie = list(range(v)) if ids_encoder is None else list(ids_encoder)
+        ir = list(range(v)) if ids_render is None else list(ids_render)
+        enc_in = images[:, ie]
+        colour_src = images_alt if images_alt is not None else images * 0.5 + 0.5
+        n, nv, c, h, w = enc_in.shape
+        flip = bool(self.flip_augmentation and self.training and (torch.rand(1) > 0.5).item())
+        x = enc_in.reshape(n * nv, c, h, w)
+        if flip:
+            x = torch.flip(x, dims=(-1,))
+        latents = self.encoder(x)
+        if flip:
+            latents = [torch.flip(l, dims=(-1,)) for l in latents]
+        h_, w_ = latents[0].shape[-2:]
+        c_l = self.encoder.latent_size
+        self.grid_f_features = [F.interpolate(l, (h_, w_)).view(n, nv, c_l, h_, w_) for l in latents]
+        self.grid_f_Ks, self.grid_f_poses_w2c, self.grid_f_combine = Ks[:, ie], w2c[:, ie], None
+        self.grid_c_imgs, self.grid_c_Ks, self.grid_c_poses_w2c, self.grid_c_combine = colour_src[:, ir], Ks[:, ir], w2c[:, ir], None
+        self._encode_gen += 1
+        self._scene_cache.clear()
+
+    def forward(self, xyz, coarse=True, viewdirs=None, far=False, only_density=False):
+        """Point query (models_bts.py:266-338): xyz (n,P,3) -> rgb (n,P,3*Vc), invalid (n,P,Vc) float, sigma (n,P,1);
+        with ``only_density`` rgb is zeros and invalid keeps the reference's (n,Vf,P,1) shape (models_bts.py:283,337)."""
+        if viewdirs is not None:
+            raise NotImplementedError("use_viewdirs is not part of the BTS field")
+        lib = _lib.load()
+        scene, keep = self._scene_struct()
+        mlp, keep2 = self._mlp_struct()
+        cfg, keep3 = self._cfg_struct(None)
+        xyz_d = _dev_f32(xyz)
+        self._require_cuda(xyz_d)
+        n, P, _ = xyz_d.shape
+        Vc, Cc = scene.Vc, scene.Cc
+        dev = xyz_d.device
+        sigma = torch.empty((n, P, 1), device=dev, dtype=torch.float32)
+        inv_f = torch.empty((n, P), device=dev, dtype=torch.float32)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if only_density:
+            rc = lib.bts_query_field(C.byref(scene), C.byref(mlp), C.byref(cfg), xyz_d.data_ptr(), n, P, sigma.data_ptr(),
+                                     inv_f.data_ptr(), None, None, stream)
+            _lib.check(rc, "bts_query_field")
+            return torch.zeros((n, P, Vc * 3), device=dev), inv_f.view(n, 1, P, 1), sigma
+        rgb = torch.empty((n, P, Vc * Cc), device=dev, dtype=torch.float32)
+        invalid = torch.empty((n, P, Vc), device=dev, dtype=torch.float32)
+        rc = lib.bts_query_field(C.byref(scene), C.byref(mlp), C.byref(cfg), xyz_d.data_ptr(), n, P, sigma.data_ptr(),
+                                 inv_f.data_ptr(), rgb.data_ptr(), invalid.data_ptr(), stream)
+        _lib.check(rc, "bts_query_field")
+        return rgb, invalid, sigma
+
+    # ------------------------------------------------------------------ CUDA plumbing
+    def invalidate_scene(self):
+        """Drop the render-ready scene (folded map, packed colours): the next call rebuilds it."""
+        self._scene_cache.clear()
+
+    @staticmethod
+    def _require_cuda(t):
+        if not t.is_cuda:
+            raise _lib.BtsCudaError("the BTS render path runs on CUDA tensors only (no CPU fallback)")
+
+    def _mlp_struct(self):
+        m = self.mlp_coarse
+        s = _lib.BtsMlp()
+        s.C, s.P, s.Hd, s.n_blocks = self.encoder.latent_size, self.code_xyz.d_out, m.d_hidden, m.n_blocks
+        if m.n_blocks > _lib.BTS_MAX_BLOCKS:
+            raise NotImplementedError(f"n_blocks={m.n_blocks} > {_lib.BTS_MAX_BLOCKS}")
+        keep = [_dev_f32(m.lin_in.weight.detach()), _dev_f32(m.lin_in.bias.detach()),
+                _dev_f32(m.lin_out.weight.detach()), _dev_f32(m.lin_out.bias.detach())]
+        self._require_cuda(keep[0])
+        s.w_in, s.b_in, s.w_out, s.b_out = (t.data_ptr() for t in keep)
+        for i, blk in enumerate(m.blocks):
+            ts = [_dev_f32(blk.fc_0.weight.detach()), _dev_f32(blk.fc_0.bias.detach()),
+                  _dev_f32(blk.fc_1.weight.detach()), _dev_f32(blk.fc_1.bias.detach())]
+            s.fc0_w[i], s.fc0_b[i], s.fc1_w[i], s.fc1_b[i] = (t.data_ptr() for t in ts)
+            keep += ts
+        return s, keep
+
+    def _cfg_struct(self, renderer):
+        c = _lib.BtsRenderCfg()
+        code = self.code_xyz
+        c.inv_z, c.code_mode, c.learn_empty = int(self.inv_z), 0 if self.code_mode == "z" else 1, int(self.learn_empty)
+        c.num_freqs, c.include_input, c.freq_factor = code.num_freqs, int(code.include_input), code.freq_factor
+        c.z_near, c.z_far = float(self.d_min), float(self.d_max)
+        # python-double scalar arithmetic of models_bts.py:160-162, rounded to fp32 once like torch does
+        c.inv_z_far = 1 / self.d_max
+        c.inv_z_range = 1 / self.d_min - 1 / self.d_max
+        c.z_range = self.d_max - self.d_min
+        keep = []
+        if renderer is not None:
+            K = int(renderer.n_coarse)
+            c.n_coarse, c.lindisp = K, int(renderer.lindisp)
+            c.hard_alpha_cap, c.white_bkgd = int(renderer.hard_alpha_cap), int(renderer.white_bkgd)
+            c.step = 1.0 / K
+            dev = self.mlp_coarse.lin_in.weight.device
+            steps = renderer._z_steps(K, dev)
+            c.z_steps = steps.data_ptr()
+            c.precision = int(getattr(renderer, "precision", 0))
+            keep.append(steps)
+        return c, keep
+
+    def _scene_struct(self):
+        """Render-ready scene for the current encode()/scale/weights; rebuilt when any of them changed."""
+        if self.grid_f_features is None:
+            raise RuntimeError("call encode() first")
+        lib = _lib.load()
+        feats = self.grid_f_features[self._scale]
+        n, nv, Cf, H, W = feats.shape
+        if nv != 1:
+            raise NotImplementedError("B200 render path implements one encoder view (ids_encoder=[0], all shipped configs)")
+        self._require_cuda(feats)
+        w_in = self.mlp_coarse.lin_in.weight
+        ef = self.empty_feature if self.learn_empty else None
+        key = (self._encode_gen, self._scale, w_in._version, w_in.data_ptr(), feats._version, feats.data_ptr(),
+               None if ef is None else (ef._version, ef.data_ptr()))
+        hit = self._scene_cache.get("scene")
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        dev = feats.device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        Hd = self.mlp_coarse.d_hidden
+        f = _dev_f32(feats.detach()).view(n, Cf, H, W)
+        w = _dev_f32(w_in.detach())
+        G = torch.empty((n, H, W, Hd), device=dev, dtype=torch.float32)
+        g_empty = torch.empty((Hd,), device=dev, dtype=torch.float32) if ef is not None else None
+        efd = _dev_f32(ef.detach()) if ef is not None else None
+        rc = lib.bts_fold_features(f.data_ptr(), n, Cf, H, W, w.data_ptr(), w.shape[1], Hd,
+                                   None if efd is None else efd.data_ptr(), G.data_ptr(),
+                                   None if g_empty is None else g_empty.data_ptr(), stream)
+        _lib.check(rc, "bts_fold_features")
+        imgs = _dev_f32(self.grid_c_imgs.detach())
+        _, Vc, Cc, Hc, Wc = imgs.shape
+        img4 = torch.empty((n, Vc, Hc, Wc, 4), device=dev, dtype=torch.float32)
+        if Vc > 0:
+            rc = lib.bts_pack_images(imgs.data_ptr(), n * Vc, Cc, Hc, Wc, img4.data_ptr(), stream)
+            _lib.check(rc, "bts_pack_images")
+        Kf = _dev_f32(self.grid_f_Ks[:, 0, :3, :3].detach())
+        Mf = _dev_f32(self.grid_f_poses_w2c[:, 0].detach())
+        Kc = _dev_f32(self.grid_c_Ks[:, :, :3, :3].detach())
+        Mc = _dev_f32(self.grid_c_poses_w2c.detach())
+        s = _lib.BtsScene()
+        s.n, s.H, s.W, s.Hd = n, H, W, Hd
+        s.G, s.g_empty = G.data_ptr(), (None if g_empty is None else g_empty.data_ptr())
+        s.K_f, s.w2c_f = Kf.data_ptr(), Mf.data_ptr()
+        s.Vc, s.Cc, s.Hc, s.Wc = Vc, Cc, Hc, Wc
+        s.img4, s.K_c, s.w2c_c = img4.data_ptr(), Kc.data_ptr(), Mc.data_ptr()
+        keep = [f, w, G, g_empty, efd, imgs, img4, Kf, Mf, Kc, Mc]
+        self._scene_cache["scene"] = (key, s, keep)
+        return s, keep
+
+    def render_rays(self, renderer, rays, u=None, seed=0, want_weights=False, want_alphas=False, want_z_samps=False,
+                    want_rgb_samps=False):
+        """Fused sampling + field + compositing for ``NeRFRenderer.forward`` (coarse pass).
+        rays (n,R,8) -> dict of fresh tensors with the reference's shapes (nerf.py:377-401)."""
+        lib = _lib.load()
+        rays_d = _dev_f32(rays)
+        self._require_cuda(rays_d)
+        scene, keep = self._scene_struct()
+        mlp, keep2 = self._mlp_struct()
+        cfg, keep3 = self._cfg_struct(renderer)
+        n, R, _ = rays_d.shape
+        K, Vc, Cc = cfg.n_coarse, scene.Vc, scene.Cc
+        dev = rays_d.device
+        new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)  # noqa: E731
+        ret = {"rgb": new(n, R, Vc * Cc), "depth": new(n, R), "invalid": new(n, R, K, Vc)}
+        if want_weights:
+            ret["weights"] = new(n, R, K)
+        if want_alphas:
+            ret["alphas"] = new(n, R, K)
+        if want_z_samps:
+            ret["z_samps"] = new(n, R, K)
+        if want_rgb_samps:
+            ret["rgb_samps"] = new(n, R, K, Vc * Cc)
+        out = _lib.BtsRenderOut()
+        for k, t in ret.items():
+            setattr(out, k, t.data_ptr())
+        u_d = None
+        if u is not None:
+            u_d = _dev_f32(u.to(dev))
+            if u_d.numel() != n * R * K:
+                raise ValueError(f"u must have n*R*K = {n * R * K} elements, got {u_d.numel()}")
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.bts_render_fwd(C.byref(scene), C.byref(mlp), C.byref(cfg), rays_d.data_ptr(), n, R,
+                                None if u_d is None else u_d.data_ptr(), int(seed) & (2 ** 64 - 1), C.byref(out), stream)
+        _lib.check(rc, "bts_render_fwd")
+        return ret

@@ -1,0 +1,119 @@
+// C ABI of libbts_b200.so (include/bts_b200.h): argument validation, kernel-family dispatch, error reporting.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace bts {
+cudaError_t launch_general(const KernelParams& p, bool points, cudaStream_t stream);
+size_t general_smem_bytes(int Hd, int p_pad, int n_blocks);
+cudaError_t launch_fold(const float* feat, int n, int C, int H, int W, const float* w_in, int ld, int Hd,
+                        const float* empty, float* G, float* g_empty, cudaStream_t stream);
+cudaError_t launch_pack_images(const float* img, int nv_total, int Cc, int Hc, int Wc, float* out, cudaStream_t stream);
+}  // namespace bts
+
+namespace {
+thread_local char g_err[512] = "";
+thread_local const char* g_kernel = "none";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_common(const BtsScene* s, const BtsMlp* m, const BtsRenderCfg* c) {
+  if (!s || !m || !c) return fail(BTS_ERR_INVALID_ARGUMENT, "null scene/mlp/cfg");
+  if (!s->G || !s->K_f || !s->w2c_f) return fail(BTS_ERR_INVALID_ARGUMENT, "scene.G / K_f / w2c_f is null");
+  if (s->Vc > 0 && (!s->img4 || !s->K_c || !s->w2c_c)) return fail(BTS_ERR_INVALID_ARGUMENT, "scene colour views are null");
+  if (s->Vc < 0 || s->Vc > bts::kMaxColorViews) return fail(BTS_ERR_UNSUPPORTED, "Vc=%d not in [0,%d]", s->Vc, bts::kMaxColorViews);
+  if (s->Cc < 1 || s->Cc > 4) return fail(BTS_ERR_UNSUPPORTED, "Cc=%d not in [1,4]", s->Cc);
+  if (s->n < 1 || s->H < 1 || s->W < 1) return fail(BTS_ERR_INVALID_ARGUMENT, "bad scene sizes");
+  if (m->Hd != s->Hd) return fail(BTS_ERR_INVALID_ARGUMENT, "mlp.Hd=%d != scene.Hd=%d", m->Hd, s->Hd);
+  if (m->Hd % 32 != 0 || m->Hd < 32 || m->Hd > 128) return fail(BTS_ERR_UNSUPPORTED, "d_hidden=%d must be 32/64/96/128", m->Hd);
+  if (m->n_blocks < 0 || m->n_blocks > BTS_MAX_BLOCKS) return fail(BTS_ERR_UNSUPPORTED, "n_blocks=%d > %d", m->n_blocks, BTS_MAX_BLOCKS);
+  if (!m->w_in || !m->b_in || !m->w_out || !m->b_out) return fail(BTS_ERR_INVALID_ARGUMENT, "mlp weights are null");
+  for (int b = 0; b < m->n_blocks; ++b)
+    if (!m->fc0_w[b] || !m->fc0_b[b] || !m->fc1_w[b] || !m->fc1_b[b]) return fail(BTS_ERR_INVALID_ARGUMENT, "block %d weights are null", b);
+  const int p_expect = 3 * 2 * c->num_freqs + (c->include_input ? 3 : 0);
+  if (m->P != p_expect) return fail(BTS_ERR_INVALID_ARGUMENT, "mlp.P=%d but code width is %d", m->P, p_expect);
+  if (c->learn_empty && !s->g_empty) return fail(BTS_ERR_INVALID_ARGUMENT, "learn_empty set but scene.g_empty is null");
+  if (c->code_mode != 0 && c->code_mode != 1) return fail(BTS_ERR_UNSUPPORTED, "code_mode=%d", c->code_mode);
+  const size_t smem = bts::general_smem_bytes(m->Hd, (m->P + 3) & ~3, m->n_blocks);
+  if (smem > 200 * 1024) return fail(BTS_ERR_UNSUPPORTED, "ResnetFC blocks (%d x %d^2) do not fit in shared memory", m->n_blocks, m->Hd);
+  return BTS_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int bts_abi_version(void) { return BTS_ABI_VERSION; }
+const char* bts_last_error(void) { return g_err; }
+const char* bts_last_kernel(void) { return g_kernel; }
+
+int bts_fold_features(const float* feat_nchw, int32_t n, int32_t C, int32_t H, int32_t W, const float* w_in,
+                      int32_t ld_w_in, int32_t Hd, const float* empty_feature_or_null, float* G_out,
+                      float* g_empty_out_or_null, bts_stream_t stream) {
+  if (!feat_nchw || !w_in || !G_out) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_fold_features: null pointer");
+  if (n < 1 || C < 1 || H < 1 || W < 1 || ld_w_in < C) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_fold_features: bad sizes");
+  if (Hd % 32 != 0 || Hd < 32 || Hd > 128) return fail(BTS_ERR_UNSUPPORTED, "d_hidden=%d must be 32/64/96/128", Hd);
+  const cudaError_t e = bts::launch_fold(feat_nchw, n, C, H, W, w_in, ld_w_in, Hd, empty_feature_or_null, G_out,
+                                         g_empty_out_or_null, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_fold_features: %s", cudaGetErrorString(e));
+  return BTS_OK;
+}
+
+int bts_pack_images(const float* img_nchw, int32_t nv_total, int32_t Cc, int32_t Hc, int32_t Wc, float* img4_out,
+                    bts_stream_t stream) {
+  if (!img_nchw || !img4_out) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_pack_images: null pointer");
+  if (Cc < 1 || Cc > 4) return fail(BTS_ERR_UNSUPPORTED, "Cc=%d not in [1,4]", Cc);
+  const cudaError_t e = bts::launch_pack_images(img_nchw, nv_total, Cc, Hc, Wc, img4_out, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_pack_images: %s", cudaGetErrorString(e));
+  return BTS_OK;
+}
+
+int bts_render_fwd(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg* cfg, const float* rays, int64_t n,
+                   int64_t R, const float* u_or_null, uint64_t seed, const BtsRenderOut* out, bts_stream_t stream) {
+  int rc = check_common(scene, mlp, cfg);
+  if (rc != BTS_OK) return rc;
+  if (!rays || !out) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_render_fwd: rays/out is null");
+  if (n != scene->n) return fail(BTS_ERR_INVALID_ARGUMENT, "rays batch %lld != scene.n %d", (long long)n, scene->n);
+  if (R < 0) return fail(BTS_ERR_INVALID_ARGUMENT, "R < 0");
+  if (cfg->n_coarse < 1 || !cfg->z_steps) return fail(BTS_ERR_INVALID_ARGUMENT, "n_coarse < 1 or z_steps null");
+  if ((out->rgb || out->invalid || out->rgb_samps) && scene->Vc < 1) return fail(BTS_ERR_INVALID_ARGUMENT, "colour outputs requested with Vc=0");
+  if (n * R == 0) return BTS_OK;
+  bts::KernelParams p;
+  memset(&p, 0, sizeof(p));
+  p.scene = *scene; p.mlp = *mlp; p.cfg = *cfg; p.out = *out;
+  p.rays = rays; p.u = u_or_null; p.n_items = n * R; p.per_batch = R; p.seed = seed;
+  p.p_pad = (mlp->P + 3) & ~3;
+  g_kernel = "general";
+  const cudaError_t e = bts::launch_general(p, false, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_render_fwd: %s", cudaGetErrorString(e));
+  return BTS_OK;
+}
+
+int bts_query_field(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg* cfg, const float* xyz, int64_t n,
+                    int64_t P, float* sigma, float* invalid_f, float* rgb_or_null, float* invalid_or_null,
+                    bts_stream_t stream) {
+  int rc = check_common(scene, mlp, cfg);
+  if (rc != BTS_OK) return rc;
+  if (!xyz || !sigma || !invalid_f) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_query_field: null pointer");
+  if (n != scene->n) return fail(BTS_ERR_INVALID_ARGUMENT, "xyz batch %lld != scene.n %d", (long long)n, scene->n);
+  if ((rgb_or_null || invalid_or_null) && scene->Vc < 1) return fail(BTS_ERR_INVALID_ARGUMENT, "colour outputs requested with Vc=0");
+  if (n * P == 0) return BTS_OK;
+  bts::KernelParams p;
+  memset(&p, 0, sizeof(p));
+  p.scene = *scene; p.mlp = *mlp; p.cfg = *cfg;
+  p.xyz = xyz; p.q_sigma = sigma; p.q_invalid_f = invalid_f; p.q_rgb = rgb_or_null; p.q_invalid = invalid_or_null;
+  p.n_items = n * P; p.per_batch = P;
+  p.p_pad = (mlp->P + 3) & ~3;
+  const cudaError_t e = bts::launch_general(p, true, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_query_field: %s", cudaGetErrorString(e));
+  return BTS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,213 @@
+// Shared device helpers for the BTS render kernels (sm_100a).
+// Every helper cites the reference lines whose arithmetic it reproduces (paths relative to the reference root).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bts_b200.h"
+
+namespace bts {
+
+constexpr float kEps = 1e-3f;            // models/bts/model/models_bts.py:14
+constexpr int kMaxColorViews = 8;
+constexpr float kPeFastLimit = 8.0f;     // |coordinate| above this -> per-term sinf (reference-exact argument)
+
+struct KernelParams {
+  BtsScene scene;
+  BtsMlp mlp;
+  BtsRenderCfg cfg;
+  BtsRenderOut out;
+  const float* rays;     // (n*R, 8)            [render]
+  const float* u;        // (n*R, K) or null    [render]
+  const float* xyz;      // (n*P, 3)            [query]
+  float* q_sigma;        // (n*P)               [query]
+  float* q_invalid_f;    // (n*P)               [query]
+  float* q_rgb;          // (n*P, Vc*Cc)|null   [query]
+  float* q_invalid;      // (n*P, Vc)|null      [query]
+  int64_t n_items;       // n*R rays or n*P points
+  int64_t per_batch;     // R or P
+  uint64_t seed;
+  int p_pad;             // P rounded up to a multiple of 4
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// Counter-based generator for the stratified jitter when the caller does not inject `u`
+// (the reference draws torch.rand_like, models/common/render/nerf.py:116).  Philox4x32-10, key = seed,
+// counter = (ray, sample/4); uniform = top 24 bits * 2^-24 in [0,1) like torch's float uniform.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+
+__device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t ray, uint32_t k) {
+  uint32_t c[4] = {(uint32_t)ray, (uint32_t)(ray >> 32), k >> 2, 0x42545342u};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  const uint32_t x = c[k & 3];
+  return (float)(x >> 8) * (1.0f / 16777216.0f);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Stratified depth of sample k on a ray (nerf.py:103-123), rounding exactly like the reference's separate
+// elementwise ops (no FMA contraction): steps = linspace[k] + u*step;  lindisp: 1/(1/near*(1-s) + 1/far*s).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sample_depth(const KernelParams& p, int64_t ray, int k, float near_, float far_) {
+  const float uu = p.u ? __ldg(p.u + ray * p.cfg.n_coarse + k) : philox_uniform(p.seed, (uint64_t)ray, (uint32_t)k);
+  const float s = __fadd_rn(__ldg(p.cfg.z_steps + k), __fmul_rn(uu, p.cfg.step));
+  const float one_m = __fsub_rn(1.0f, s);
+  if (p.cfg.lindisp) {
+    const float a = __fmul_rn(__fdiv_rn(1.0f, near_), one_m);
+    const float b = __fmul_rn(__fdiv_rn(1.0f, far_), s);
+    return __fdiv_rn(1.0f, __fadd_rn(a, b));
+  }
+  return __fadd_rn(__fmul_rn(near_, one_m), __fmul_rn(far_, s));
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Pinhole projection of a world point into one view (models_bts.py:145-155 / :221-232):
+//   cam = M[:3,:] @ [x;1];  dist = |cam|;  (a,b,c) = K @ cam;  uv = (a,b)/max(c,EPS);  invalid = c<=EPS | |u|>1 | |v|>1
+// ------------------------------------------------------------------------------------------------------------------
+struct View {
+  float K[9];
+  float M[12];
+};
+
+__device__ __forceinline__ void load_view(View& v, const float* __restrict__ K33, const float* __restrict__ M44) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) v.K[i] = __ldg(K33 + i);
+#pragma unroll
+  for (int i = 0; i < 12; ++i) v.M[i] = __ldg(M44 + i);
+}
+
+struct Proj {
+  float u, v, c, dist;
+  bool invalid;
+};
+
+__device__ __forceinline__ float dot4(const float* m, float x, float y, float z) {
+  float a = m[0] * x;
+  a = fmaf(m[1], y, a);
+  a = fmaf(m[2], z, a);
+  return a + m[3];
+}
+__device__ __forceinline__ float dot3(const float* m, float x, float y, float z) {
+  float a = m[0] * x;
+  a = fmaf(m[1], y, a);
+  return fmaf(m[2], z, a);
+}
+
+__device__ __forceinline__ Proj project(const View& vw, float x, float y, float z) {
+  Proj r;
+  const float cx = dot4(vw.M + 0, x, y, z), cy = dot4(vw.M + 4, x, y, z), cz = dot4(vw.M + 8, x, y, z);
+  r.dist = sqrtf(fmaf(cz, cz, fmaf(cy, cy, cx * cx)));
+  const float a = dot3(vw.K + 0, cx, cy, cz), b = dot3(vw.K + 3, cx, cy, cz);
+  r.c = dot3(vw.K + 6, cx, cy, cz);
+  const float den = fmaxf(r.c, kEps);
+  r.u = __fdiv_rn(a, den);
+  r.v = __fdiv_rn(b, den);
+  r.invalid = (r.c <= kEps) | (r.u < -1.0f) | (r.u > 1.0f) | (r.v < -1.0f) | (r.v > 1.0f);
+  return r;
+}
+
+// Depth code in [-1,1] (models_bts.py:157-171); python-scalar constants pre-rounded on the host.
+__device__ __forceinline__ float depth_code(const BtsRenderCfg& cfg, const Proj& pr) {
+  const float zeta = cfg.code_mode == 0 ? pr.c : pr.dist;
+  float t;
+  if (cfg.inv_z) {
+    t = __fdiv_rn(__fsub_rn(__fdiv_rn(1.0f, fmaxf(zeta, kEps)), cfg.inv_z_far), cfg.inv_z_range);
+  } else {
+    t = __fdiv_rn(__fsub_rn(zeta, cfg.z_near), cfg.z_range);
+  }
+  return __fsub_rn(__fmul_rn(2.0f, t), 1.0f);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Bilinear tap set of F.grid_sample(mode="bilinear", padding_mode="border", align_corners=False)
+// (models_bts.py:179, :234):  ix = ((u+1)*W-1)/2 clipped to [0,W-1]; taps floor(ix), +1 (clamped; its weight is 0 there).
+// ------------------------------------------------------------------------------------------------------------------
+struct Taps {
+  int x0, y0, dx, dy;          // dx in {0,1}, dy in {0,1}: clamped neighbour offsets
+  float wx0, wx1, wy0, wy1;
+};
+
+__device__ __forceinline__ void axis_taps(float coord, int size, int& i0, int& d, float& w0, float& w1) {
+  float ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(coord, 1.0f), (float)size), 1.0f), 0.5f);
+  ix = fminf(fmaxf(ix, 0.0f), (float)(size - 1));
+  const float f = floorf(ix);
+  w1 = ix - f;
+  w0 = (f + 1.0f) - ix;
+  i0 = (int)f;
+  d = (i0 + 1 < size) ? 1 : 0;
+}
+
+__device__ __forceinline__ Taps bilinear_taps(float u, float v, int H, int W) {
+  Taps t;
+  axis_taps(u, W, t.x0, t.dx, t.wx0, t.wx1);
+  axis_taps(v, H, t.y0, t.dy, t.wy0, t.wy1);
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Positional code of (u, v, zhat) (models/common/model/code.py:30-42): out = [x, sin(f0 x), sin(f0 x + pi/2), ...],
+// octave-major, then (sin,cos), then dim; the reference evaluates sin(fma(x, f_i, phase)) (torch.addcmul is a fused
+// multiply-add on CPU and GPU).  Fast path: one accurate sincosf at the base octave, then exact double-angle steps
+// (error grows ~2x per octave, like the reference's own argument rounding).  Coordinates beyond kPeFastLimit
+// (samples far outside the frustum / behind the camera, clamped z) take the per-term path so the huge arguments are
+// rounded exactly like the reference's.  `dst[j * stride]` receives code entry j.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void positional_code(const BtsRenderCfg& cfg, float p0, float p1, float p2, float* dst,
+                                                int stride) {
+  const float pv[3] = {p0, p1, p2};
+  int off = 0;
+  if (cfg.include_input) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) dst[d * stride] = pv[d];
+    off = 3;
+  }
+  const float kHalfPi = 1.57079637050628662109375f;  // float32(np.pi * 0.5), code.py:27
+  const bool big = fmaxf(fabsf(p0), fmaxf(fabsf(p1), fabsf(p2))) > kPeFastLimit;
+  if (!big) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      float s, c;
+      sincosf(__fmul_rn(pv[d], cfg.freq_factor), &s, &c);
+      for (int i = 0; i < cfg.num_freqs; ++i) {
+        dst[(off + i * 6 + d) * stride] = s;
+        dst[(off + i * 6 + 3 + d) * stride] = c;
+        const float s2 = 2.0f * s * c;
+        c = (c - s) * (c + s);
+        s = s2;
+      }
+    }
+  } else {
+    float f = cfg.freq_factor;
+    for (int i = 0; i < cfg.num_freqs; ++i) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        dst[(off + i * 6 + d) * stride] = sinf(__fmul_rn(pv[d], f));
+        dst[(off + i * 6 + 3 + d) * stride] = sinf(fmaf(pv[d], f, kHalfPi));
+      }
+      f *= 2.0f;
+    }
+  }
+}
+
+__device__ __forceinline__ float softplus(float x) {  // F.softplus beta=1 threshold=20 (models_bts.py:313)
+  return x > 20.0f ? x : log1pf(expf(x));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace bts

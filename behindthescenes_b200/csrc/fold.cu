@@ -1,0 +1,119 @@
+// Encode-side glue kernels (run once per encode()/weight update, not per ray):
+//   fold_features : G[b, p, :] = W_in[:, :C] * F[b, :, p]   -- layer-1 linearity: bilinear
+//                   interpolation commutes with the feature part of lin_in, so the render kernels interpolate the
+//                   Hd-channel map G instead of the C-channel map F and only contract the 39-wide positional code
+//                   per sample.  fp32, k-sequential FMA accumulation.
+//   pack_images   : colour views NCHW -> channels-last padded to 4 (one 16-byte load per bilinear tap).
+// Reference tensors: grid_f_features / grid_c_imgs as cached by BTSNet.encode (models/bts/model/models_bts.py:126-136);
+// weight = mlp_coarse.lin_in.weight[:, :C] (models/common/model/resnetfc.py:88, input order models_bts.py:184).
+#include "common.cuh"
+
+namespace bts {
+
+constexpr int kFoldPix = 128;   // pixels per CTA
+constexpr int kFoldCk = 32;     // channels per shared-memory stage
+
+template <int UN>  // units per thread; Hd = 8 * UN
+__global__ void __launch_bounds__(256) fold_features_kernel(const float* __restrict__ feat, int C, int64_t HW,
+                                                            const float* __restrict__ w_in, int ld, float* __restrict__ G) {
+  constexpr int Hd = 8 * UN;
+  __shared__ __align__(16) float Fs[kFoldCk][kFoldPix];
+  __shared__ __align__(16) float Ws[kFoldCk][Hd];
+  const int b = blockIdx.y;
+  const int64_t p0 = (int64_t)blockIdx.x * kFoldPix;
+  const int tp = threadIdx.x & 31, tn = threadIdx.x >> 5;
+  float acc[4][UN];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int n = 0; n < UN; ++n) acc[i][n] = 0.0f;
+  const float* fb = feat + (size_t)b * C * HW;
+  for (int c0 = 0; c0 < C; c0 += kFoldCk) {
+    for (int i = threadIdx.x; i < kFoldCk * kFoldPix; i += 256) {
+      const int c = i / kFoldPix, px = i % kFoldPix;
+      const int64_t pp = p0 + px;
+      Fs[c][px] = (c0 + c < C && pp < HW) ? __ldg(fb + (size_t)(c0 + c) * HW + pp) : 0.0f;
+    }
+    for (int i = threadIdx.x; i < kFoldCk * Hd; i += 256) {
+      const int n = i / kFoldCk, c = i % kFoldCk;
+      Ws[c][n] = (c0 + c < C) ? __ldg(w_in + (size_t)n * ld + c0 + c) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int c = 0; c < kFoldCk; ++c) {
+      const float4 f = *reinterpret_cast<const float4*>(&Fs[c][tp * 4]);
+      float w[UN];
+#pragma unroll
+      for (int n = 0; n < UN; n += 4) {
+        const float4 q = *reinterpret_cast<const float4*>(&Ws[c][tn * UN + n]);
+        w[n] = q.x; w[n + 1] = q.y; w[n + 2] = q.z; w[n + 3] = q.w;
+      }
+      const float fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int n = 0; n < UN; ++n) acc[i][n] = fmaf(w[n], fv[i], acc[i][n]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t pp = p0 + tp * 4 + i;
+    if (pp < HW) {
+      float* o = G + ((size_t)b * HW + pp) * Hd + tn * UN;
+#pragma unroll
+      for (int n = 0; n < UN; n += 4) *reinterpret_cast<float4*>(o + n) = make_float4(acc[i][n], acc[i][n + 1], acc[i][n + 2], acc[i][n + 3]);
+    }
+  }
+}
+
+__global__ void fold_empty_kernel(const float* __restrict__ empty, int C, const float* __restrict__ w_in, int ld, int Hd,
+                                  float* __restrict__ g_empty) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= Hd) return;
+  float a = 0.0f;
+  for (int c = 0; c < C; ++c) a = fmaf(__ldg(w_in + (size_t)n * ld + c), __ldg(empty + c), a);
+  g_empty[n] = a;
+}
+
+__global__ void pack_images_kernel(const float* __restrict__ img, int Cc, int64_t HW, int64_t total, float4* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t v = i / HW, px = i % HW;
+  const float* src = img + (size_t)v * Cc * HW + px;
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  o.x = __ldg(src);
+  if (Cc > 1) o.y = __ldg(src + HW);
+  if (Cc > 2) o.z = __ldg(src + 2 * HW);
+  if (Cc > 3) o.w = __ldg(src + 3 * HW);
+  out[i] = o;
+}
+
+cudaError_t launch_fold(const float* feat, int n, int C, int H, int W, const float* w_in, int ld, int Hd,
+                        const float* empty, float* G, float* g_empty, cudaStream_t stream) {
+  const int64_t HW = (int64_t)H * W;
+  dim3 grid((unsigned)((HW + kFoldPix - 1) / kFoldPix), (unsigned)n);
+  switch (Hd / 8) {
+    case 4: fold_features_kernel<4><<<grid, 256, 0, stream>>>(feat, C, HW, w_in, ld, G); break;
+    case 8: fold_features_kernel<8><<<grid, 256, 0, stream>>>(feat, C, HW, w_in, ld, G); break;
+    case 12: fold_features_kernel<12><<<grid, 256, 0, stream>>>(feat, C, HW, w_in, ld, G); break;
+    case 16: fold_features_kernel<16><<<grid, 256, 0, stream>>>(feat, C, HW, w_in, ld, G); break;
+    default: return cudaErrorInvalidValue;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (empty && g_empty) {
+    fold_empty_kernel<<<(Hd + 127) / 128, 128, 0, stream>>>(empty, C, w_in, ld, Hd, g_empty);
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+cudaError_t launch_pack_images(const float* img, int nv_total, int Cc, int Hc, int Wc, float* out, cudaStream_t stream) {
+  const int64_t HW = (int64_t)Hc * Wc, total = HW * nv_total;
+  if (total == 0) return cudaSuccess;
+  pack_images_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(img, Cc, HW, total, reinterpret_cast<float4*>(out));
+  return cudaGetLastError();
+}
+
+}  // namespace bts

@@ -190,3 +190,41 @@ def cfg5_stress(R=4096 * 4096, H=192, W=640, K=256, d_hidden=128, seed=0) -> Wor
     wl.rays = torch.cat((o, d, nf), -1).view(1, R, 8).contiguous()
     wl.u = None  # too large to inject; perf mode uses the in-kernel generator
     return wl
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# Model construction for synthetic workloads (tests, bench, smoke)
+# --------------------------------------------------------------------------------------------------------------------
+
+class FeatureEncoder(torch.nn.Module):
+    """Encoder stand-in that returns a fixed feature tensor (the reference's own overfit harness does the same:
+    ``models/bts/trainer_overfit.py:24-33``).  The render path only consumes the encoder's output layout
+    (n*nv, C, H, W); the ResNet itself is out of scope (SURVEY.md §2 #6)."""
+
+    def __init__(self, feats: torch.Tensor):
+        super().__init__()
+        self.feats = torch.nn.Parameter(feats.clone(), requires_grad=False)
+        self.latent_size = feats.shape[1]
+        self.scales = [0]
+
+    def forward(self, x):
+        return [self.feats]
+
+
+def build_model(wl: Workload, device, state_dict=None):
+    """(net, wrapped_renderer) for a workload; weights from ``state_dict`` (reference keys) or the reference's init
+    scheme under ``wl.weight_seed``."""
+    from . import BTSNet, NeRFRenderer
+    torch.manual_seed(wl.weight_seed)
+    net = BTSNet(wl.model_conf, encoder=FeatureEncoder(wl.feats))
+    if state_dict is not None:
+        missing, unexpected = net.load_state_dict(state_dict, strict=False)
+        assert not unexpected, unexpected
+        assert all(k.startswith("encoder.") for k in missing), missing
+    else:
+        with torch.no_grad():
+            net.mlp_coarse.lin_out.bias.fill_(wl.lin_out_bias)
+    renderer = NeRFRenderer.from_conf(wl.renderer_conf)
+    net = net.to(device)
+    wrapped = renderer.bind_parallel(net, gpus=None).eval().to(device)
+    return net, wrapped

@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- rays/s (64 samples/ray) of the BTS render hot path on N B200s (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5              # our CUDA path (one JSON line on stdout)
+    python bench.py --impl reference --steps 3 --warmup 1       # the reference algorithm on the host CPU (oracle port)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...       # one rank per GPU, ray-sharded, weak scaling
+
+Workload at N=1 = BASELINE config 2 ("KITTI-360 eval_depth: 192x640, 64 samples/ray"): one stereo frame as
+``models/bts/evaluator.py:62-68`` renders it -- rays of both views (245 760 rays), encoder view 0, one colour view,
+``want_weights=True, want_alphas=True``.  A step = one pass of the hot path over that ray batch: fold of the frame's
+feature map (our per-frame glue), colour packing and the fused render launch.  ``encode`` (the ResNet) is excluded
+from the metric as in BASELINE.md.  At N>1 every rank renders its own block of an N-times larger global ray batch
+(``behindthescenes_b200.rays.shard_rays``; scene replicated) and the per-step scalar metric is all-reduced over NCCL.
+
+Timing: per-step CUDA events on the launching stream (torch's current stream), an L2 flush (256 MiB write) before
+every timed step outside the event pair, max over ranks.  See DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from behindthescenes_b200 import synthetic as syn  # noqa: E402
+
+METRIC = "rays/s (64 samples/ray)"
+K_SAMPLES = 64
+# SURVEY.md §8d algorithmic figures for config 2 outputs (rgb, depth, invalid, weights, alphas; one ray per pixel)
+BYTES_PER_RAY = 32 + 4 * 64 + 12 + 4 + 12 + 3 * 4 * K_SAMPLES      # = 1084 B
+DENSE_FLOP_PER_RAY = K_SAMPLES * (2 * (64 + 39) * 64 + 2 * 64)       # = 0.852 MFLOP (MLP 103->64->1)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured (MEASURED_PEAKS.json; sustained bf16)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def make_workload(args):
+    wl = syn.cfg2_kitti360_eval(H=192, W=640, K=K_SAMPLES, stereo=True, learn_empty=True, lin_out_bias=-4.0, seed=0)
+    return wl
+
+
+def weights_state_dict(wl):
+    net, _ = syn.build_model(wl, "cpu")
+    return {k: v.clone() for k, v in net.state_dict().items() if not k.startswith("encoder.")}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference algorithm (oracle port) on the host cores
+# ---------------------------------------------------------------------------------------------------------------------
+
+def cpu_reference_run(wl, sd, n_rays, steps, warmup):
+    from oracle import bts_oracle as orc
+    from tests.golden_io import mlp_params
+    torch.set_num_threads(os.cpu_count() or 1)
+    st = orc.encode_state(wl.images, wl.Ks, wl.poses_c2w, wl.feats, wl.ids_encoder, wl.ids_render)
+    fcfg = orc.FieldConfig.from_model_conf(wl.model_conf)
+    rcfg = orc.RenderConfig.from_renderer_conf(wl.renderer_conf)
+    rays = wl.rays[:, :n_rays].contiguous()
+    u = wl.u[:n_rays].contiguous()
+    mlp = mlp_params(sd)
+    out = None
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            out = orc.render(st, mlp, fcfg, rcfg, rays, u=u, empty_feature=sd.get("empty_feature"),
+                             want_weights=True, want_alphas=True)["coarse"]
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), out
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    wl = make_workload(args)
+    sd = weights_state_dict(wl)
+    n_rays = 15360                                   # 1/16 of the stereo frame per step (bounded sample)
+    sec, _ = cpu_reference_run(wl, sd, n_rays, args.steps, args.warmup)
+    v = n_rays / sec
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded frustum, randn features in place of the encoder output)",
+            "config": {"workload": "cfg2 KITTI-360 eval_depth 192x640 K=64 stereo frame; reference algorithm on host CPU",
+                       "rays_per_step": n_rays, "samples_per_ray": K_SAMPLES},
+            "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
+                             "sample": f"{n_rays} of the frame's 245760 rays per step, K=64, torch CPU ops chunked by 100000 points like nerf.py:244-268"},
+            "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for nme, val in zip(names, r[4:8]):
+                    if val.strip().lower() == "active":
+                        reasons.add(nme)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load" = samples in the upper half of the power range
+        thr = (max(pw) + min(pw)) / 2
+        load = sorted(s for s, w in zip(sm, pw) if w >= thr) or sorted(sm)
+        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(pw)}
+
+
+def run_ours(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the render path has no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from behindthescenes_b200 import _lib
+    from behindthescenes_b200 import rays as R
+    lib = _lib.load()
+
+    wl = make_workload(args)
+    sd = weights_state_dict(wl)
+    net, wrapped = syn.build_model(wl, dev, state_dict=sd)
+    wrapped.renderer.precision = args.precision
+    frame_rays = wl.rays                                              # (1, 245760, 8) host
+    n_frame = frame_rays.shape[1]
+    # global ray batch = `world` frames' worth, sharded contiguously; every rank holds the replicated scene
+    lo, hi = R.shard_bounds(n_frame * world, rank, world)
+    rays_host = frame_rays.repeat(1, world, 1)[:, lo:hi].contiguous().pin_memory()
+    rays_dev = rays_host.to(dev)
+    n_rays = rays_dev.shape[1]
+    with torch.no_grad():
+        net.encode(wl.images.to(dev), wl.Ks.to(dev), wl.poses_c2w.to(dev), ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    wants = dict(want_weights=True, want_alphas=True)
+
+    def one_step(timed, ev=None):
+        flush.fill_(1)                                                 # evict L2 (126 MB) -- outside the event pair
+        net.invalidate_scene()                                         # a new frame: fold + pack run again
+        if ev:
+            ev[0].record()
+        net._scene_struct()
+        if ev:
+            ev[1].record()
+        out = wrapped(rays_dev, **wants)["coarse"]
+        metric = {"depth_sum": out["depth"].sum(), "rays": torch.tensor(float(n_rays), device=dev)}
+        metric = R.allreduce_sums(metric)
+        if ev:
+            ev[2].record()
+        return out, metric
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            one_step(False)
+        sync_all()
+        sampler = ClockSampler(local) if rank == 0 else None
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+        t_wall0 = time.perf_counter()
+        for i in range(args.steps):
+            out, metric = one_step(True, evs[i])
+        sync_all()
+        wall = time.perf_counter() - t_wall0
+        clocks = sampler.stop() if sampler else None
+    prep_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
+    render_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps      # includes the tiny depth-sum + all-reduce
+    step_ms = sum(e[0].elapsed_time(e[2]) for e in evs) / args.steps
+    kernel_name = lib.bts_last_kernel().decode()
+
+    # ---- dominant kernel alone (roofline): the fused render launch, scene cached, events around the launch only ----
+    with torch.no_grad():
+        kev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+        for i in range(args.steps):
+            flush.fill_(1)
+            kev[i][0].record()
+            wrapped(rays_dev, **wants)
+            kev[i][1].record()
+        torch.cuda.synchronize(dev)
+    kern_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+
+    # ---- end to end through the public API with HOST buffers -----------------------------------------------------------
+    depth_host = torch.empty((1, n_rays), dtype=torch.float32).pin_memory()
+    rgb_host = torch.empty((1, n_rays, 3), dtype=torch.float32).pin_memory()
+    rays_stage = torch.empty_like(rays_dev)
+    e2e_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+    with torch.no_grad():
+        for i in range(-3, args.steps):
+            flush.fill_(1)
+            net.invalidate_scene()
+            if i >= 0:
+                e2e_ev[i][0].record()
+            rays_stage.copy_(rays_host, non_blocking=True)               # H2D of this step's rays (pinned)
+            o = wrapped(rays_stage, **wants)["coarse"]
+            depth_host.copy_(o["depth"], non_blocking=True)              # D2H of the per-ray result
+            rgb_host.copy_(o["rgb"], non_blocking=True)
+            if i >= 0:
+                e2e_ev[i][1].record()
+            torch.cuda.synchronize(dev)
+        sync_all()
+    e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_ev) / args.steps
+
+    # ---- max over ranks ----------------------------------------------------------------------------------------------
+    t = torch.tensor([step_ms, e2e_ms, kern_ms, prep_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms, e2e_ms, kern_ms_max, prep_ms = (float(x) for x in t.tolist())
+    total_rays = n_frame * world
+    value = total_rays / (step_ms * 1e-3)
+    e2e_value = total_rays / (e2e_ms * 1e-3)
+
+    line = None
+    if rank == 0:
+        pk = peaks()
+        rps_kernel = n_rays / (kern_ms * 1e-3)
+        hbm_ach = rps_kernel * BYTES_PER_RAY / 1e9
+        tf_ach = rps_kernel * DENSE_FLOP_PER_RAY / 1e12
+        f_h, f_t = hbm_ach / pk["hbm_gbs"], tf_ach / pk["tflops"]
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.isfile(tp):
+            traffic = json.load(open(tp)).get(kernel_name)
+        if f_t >= f_h:
+            roof = {"bound": "tensor", "achieved": tf_ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": f_t}
+        else:
+            roof = {"bound": "hbm", "achieved": hbm_ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": f_h}
+        roof.update({"traffic": traffic, "kernel": f"render_{kernel_name}", "kernel_ms": kern_ms, "peak_source": pk["source"],
+                     "hbm_frac": f_h, "tensor_frac": f_t, "algorithmic_bytes_per_ray": BYTES_PER_RAY,
+                     "algorithmic_dense_flop_per_ray": DENSE_FLOP_PER_RAY})
+        line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic (seeded KITTI-shaped frustum; randn features stand in for the encoder output, random-init MLP)",
+                "config": {"workload": "cfg2 KITTI-360 eval_depth: 192x640 stereo frame, 245760 rays/GPU, K=64, outputs rgb+depth+invalid+weights+alphas",
+                           "rays_per_gpu": n_rays, "samples_per_ray": K_SAMPLES, "parallelism": f"ray-shard x{world}",
+                           "l2": "256 MiB flush before every timed step", "precision_tier": "exact-fp32" if args.precision == 0 else "fast",
+                           "kernel": kernel_name, "ms_fold_pack": prep_ms, "ms_render": render_ms},
+                "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": int(rays_host.numel() * 4),
+                        "d2h_bytes_per_step": int(depth_host.numel() * 4 + rgb_host.numel() * 4), "ms_per_step": e2e_ms},
+                "gpu_launches": args.steps * (3 + 1),          # fold, fold_empty, pack_images, render per step (ours)
+                "roofline": roof, "clocks": clocks, "wall_s_timed_loop": wall,
+                "depth_sum_check": float(metric["depth_sum"].item())}
+        if world == 1 and not args.no_cpu_baseline:
+            # reference algorithm on this box's host cores, bounded sample, + depth abs_rel of our path vs it (same u)
+            n_s = 61440
+            sec, ref_out = cpu_reference_run(wl, sd, n_s, 1, 1)
+            with torch.no_grad():
+                net.invalidate_scene()
+                ours = wrapped(rays_dev[:, :n_s].contiguous(), u=wl.u[:n_s].to(dev), **wants)["coarse"]
+            d, dr = ours["depth"].cpu(), ref_out["depth"]
+            same = (ours["invalid"].cpu() == ref_out["invalid"]).flatten(2).all(-1)
+            rel = (d - dr).abs() / dr
+            line["cpu_baseline"] = {"value": n_s / sec, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"first {n_s} rays of the frame (K=64), one timed pass after one warm-up; torch CPU ops chunked like nerf.py:244-268"}
+            line["depth_abs_rel_vs_ref"] = {"all_rays": rel.mean().item(), "rays_without_knife_edge_flag_flip": rel[same].mean().item(),
+                                            "max_abs_weights": (ours["weights"].cpu() - ref_out["weights"])[same].abs().max().item(),
+                                            "rays": n_s, "flag_flip_rays": int((~same).sum().item())}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", type=int, default=0, help="0 exact-fp32 tier, 1 fast tier")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,143 @@
+/*
+ * bts_b200.h -- C ABI of the B200-native BehindTheScenes render path (libbts_b200.so).
+ *
+ * The reference (Brummi/BehindTheScenes) is pure Python/PyTorch and has no FFI layer; its seam for this path is the
+ * Python object contract of BTSNet / NeRFRenderer / _RenderWrapper.  This header is the boundary a
+ * binding would target: plain pointers + sizes + a cudaStream_t, no torch types.  Every entry point cites the
+ * reference interface it replaces (paths relative to the reference root).  All pointers are DEVICE pointers unless
+ * stated otherwise, all tensors contiguous fp32, all calls asynchronous on `stream` (no internal sync, no host
+ * allocation on the call path).  Return value: 0 on success, negative BtsStatus otherwise; the text of the last error
+ * of the calling thread is available from bts_last_error().
+ *
+ * Data layout in HBM (what "encode" leaves resident for the render kernels):
+ *   G      (n, H, W, Hd)      "folded feature map": G[p] = W_in[:, :C] * F[:, p]   (bts_fold_features)
+ *   g_empty(Hd)               W_in[:, :C] * empty_feature                            (learn_empty)
+ *   img4   (n, Vc, Hc, Wc, 4) colour views, channels-last padded to 4                (bts_pack_images)
+ *   K_*    (n, V, 3, 3), w2c_* (n, V, 4, 4) row-major camera matrices as the reference caches them
+ */
+#ifndef BTS_B200_H_
+#define BTS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BTS_ABI_VERSION 1
+#define BTS_MAX_BLOCKS 8   /* ResnetFC blocks supported by the kernels */
+
+typedef struct CUstream_st* bts_stream_t; /* == cudaStream_t */
+
+typedef enum {
+  BTS_OK = 0,
+  BTS_ERR_INVALID_ARGUMENT = -1,  /* null pointer / bad size                                  */
+  BTS_ERR_UNSUPPORTED = -2,       /* configuration the CUDA path does not implement (raises)  */
+  BTS_ERR_CUDA = -3               /* a CUDA runtime call or launch failed                      */
+} BtsStatus;
+
+/* Scene = what BTSNet.encode caches (models/bts/model/models_bts.py:128-136), in render-ready layout. */
+typedef struct {
+  int32_t n;            /* batch ("super-batch") size                                  */
+  int32_t H, W;         /* feature-map size (scale-0 map is full resolution, :125-126) */
+  int32_t Hd;           /* folded channels == mlp_coarse.d_hidden                       */
+  const float* G;       /* (n, H, W, Hd)                                                */
+  const float* g_empty; /* (Hd) or NULL when learn_empty is off                         */
+  const float* K_f;     /* (n, 3, 3)  grid_f_Ks of the single encoder view              */
+  const float* w2c_f;   /* (n, 4, 4)  grid_f_poses_w2c                                  */
+  int32_t Vc;           /* colour/render views (grid_c_imgs.shape[1])                   */
+  int32_t Cc;           /* colour channels per view (3; 4 with auto-masking), <= 4      */
+  int32_t Hc, Wc;
+  const float* img4;    /* (n, Vc, Hc, Wc, 4), values as cached by encode ([0,1])       */
+  const float* K_c;     /* (n, Vc, 3, 3)                                                */
+  const float* w2c_c;   /* (n, Vc, 4, 4)                                                */
+} BtsScene;
+
+/* MLP = ResnetFC parameters (models/common/model/resnetfc.py:66-184), d_latent = 0, ReLU, d_out = 1.
+ * lin_in.weight is (Hd, C + P): its first C columns are consumed by bts_fold_features, the render kernels read the
+ * last P columns (the positional-code part, models/bts/model/models_bts.py:184 puts features first, code last). */
+typedef struct {
+  int32_t C;            /* encoder.latent_size                                          */
+  int32_t P;            /* positional code width = d_in*(2*num_freqs) (+ d_in)          */
+  int32_t Hd;           /* d_hidden (multiple of 32, <= 128)                            */
+  int32_t n_blocks;     /* <= BTS_MAX_BLOCKS                                            */
+  const float* w_in;    /* (Hd, C + P) row-major                                        */
+  const float* b_in;    /* (Hd)                                                         */
+  const float* fc0_w[BTS_MAX_BLOCKS]; /* (Hd, Hd) each */
+  const float* fc0_b[BTS_MAX_BLOCKS];
+  const float* fc1_w[BTS_MAX_BLOCKS];
+  const float* fc1_b[BTS_MAX_BLOCKS];
+  const float* w_out;   /* (1, Hd)                                                      */
+  const float* b_out;   /* (1)                                                          */
+} BtsMlp;
+
+/* Field + renderer configuration: BTSNet.__init__ (models_bts.py:21-40), PositionalEncoding (code.py:12-28),
+ * NeRFRenderer.__init__ (models/common/render/nerf.py:66-101). */
+typedef struct {
+  int32_t n_coarse;        /* K samples per ray                                          */
+  int32_t lindisp;         /* nerf.py:117-120                                            */
+  int32_t hard_alpha_cap;  /* nerf.py:285-286                                            */
+  int32_t white_bkgd;      /* nerf.py:301-304                                            */
+  int32_t inv_z;           /* models_bts.py:159-163                                      */
+  int32_t code_mode;       /* 0 = "z", 1 = "distance" (models_bts.py:157-171)            */
+  int32_t learn_empty;     /* models_bts.py:181-182 (needs scene.g_empty)                */
+  int32_t num_freqs;       /* code.py:14                                                 */
+  int32_t include_input;   /* code.py:17                                                 */
+  float freq_factor;       /* code.py:15                                                 */
+  float z_near, z_far;     /* BTSNet.d_min / d_max (for the depth code, not the ray)     */
+  /* host-precomputed fp32 constants so the kernel rounds exactly like the reference's python-scalar arithmetic:   */
+  float inv_z_far;         /* float(1 / d_max)                       models_bts.py:160   */
+  float inv_z_range;       /* float(1 / d_min - 1 / d_max)                               */
+  float z_range;           /* float(d_max - d_min)                   models_bts.py:162   */
+  const float* z_steps;    /* (K) device: torch.linspace(0, 1 - 1/K, K)   nerf.py:114    */
+  float step;              /* float(1.0 / K)                              nerf.py:112    */
+  int32_t precision;       /* 0 = exact fp32 tier, 1 = fast (single-pass tensor-core) tier */
+} BtsRenderCfg;
+
+/* Optional outputs of NeRFRenderer._format_outputs (nerf.py:377-401).  NULL = not wanted (not computed/written). */
+typedef struct {
+  float* rgb;        /* (n, R, Vc*Cc)     view-major (models_bts.py:330)                */
+  float* depth;      /* (n, R)                                                          */
+  float* invalid;    /* (n, R, K, Vc)     0/1                                           */
+  float* weights;    /* (n, R, K)                                                       */
+  float* alphas;     /* (n, R, K)                                                       */
+  float* z_samps;    /* (n, R, K)                                                       */
+  float* rgb_samps;  /* (n, R, K, Vc*Cc)                                                */
+} BtsRenderOut;
+
+int bts_abi_version(void);
+const char* bts_last_error(void);
+
+/* Encode-side glue, once per encode() / weight update (SURVEY.md §7 "layer-1 linearity"):
+ *   G[b, y, x, :] = w_in[:, :C] * feat[b, :, y, x];   g_empty = w_in[:, :C] * empty_feature  (if non-NULL).
+ * feat is the encoder output exactly as BTSNet.encode caches it: (n, C, H, W) NCHW (models_bts.py:126-128). */
+int bts_fold_features(const float* feat_nchw, int32_t n, int32_t C, int32_t H, int32_t W, const float* w_in,
+                      int32_t ld_w_in, int32_t Hd, const float* empty_feature_or_null, float* G_out,
+                      float* g_empty_out_or_null, bts_stream_t stream);
+
+/* (n, Vc, Cc, Hc, Wc) NCHW colour views (grid_c_imgs, models_bts.py:133) -> (n, Vc, Hc, Wc, 4) channels-last. */
+int bts_pack_images(const float* img_nchw, int32_t nv_total, int32_t Cc, int32_t Hc, int32_t Wc, float* img4_out,
+                    bts_stream_t stream);
+
+/* Replaces _RenderWrapper.forward -> NeRFRenderer.forward -> sample_coarse + composite -> BTSNet.forward
+ * (nerf.py:19-45, :315-375, :103-123, :210-313; models_bts.py:266-338) for the coarse pass.
+ * rays (n, R, 8) = [origin, direction, near, far]; u (n*R, K) stratified jitter in [0,1) or NULL to draw it in-kernel
+ * from a counter-based generator keyed by (seed, ray, sample) (the reference draws torch.rand_like, nerf.py:116). */
+int bts_render_fwd(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg* cfg, const float* rays, int64_t n,
+                   int64_t R, const float* u_or_null, uint64_t seed, const BtsRenderOut* out, bts_stream_t stream);
+
+/* Replaces a direct BTSNet.forward(xyz, only_density=...) point query (models_bts.py:266-338; callers
+ * scripts/inference_setup.py:214, models/bts/evaluator_lidar.py:305).  xyz (n, P, 3).
+ * sigma (n, P); invalid_f (n, P) feature-view flag; rgb (n, P, Vc*Cc) and invalid (n, P, Vc) may be NULL
+ * (only_density). */
+int bts_query_field(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg* cfg, const float* xyz, int64_t n,
+                    int64_t P, float* sigma, float* invalid_f, float* rgb_or_null, float* invalid_or_null,
+                    bts_stream_t stream);
+
+/* Name of the kernel family the last bts_render_fwd on this thread dispatched to ("general" | "tc"), for tests. */
+const char* bts_last_kernel(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BTS_B200_H_ */

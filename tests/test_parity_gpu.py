@@ -1,0 +1,151 @@
+"""GPU: the CUDA render path (through the drop-in classes -> ctypes -> C ABI) against
+(a) the committed fixtures produced by the UNMODIFIED reference and (b) the oracle at the BASELINE sizes."""
+import pytest
+import torch
+
+from behindthescenes_b200 import _lib
+from behindthescenes_b200 import synthetic as syn
+from oracle import bts_oracle as orc
+from tests import parity_util as pu
+from tests.golden_io import golden_names, load_golden, mlp_params
+
+pytestmark = pytest.mark.gpu
+ALL = dict(want_weights=True, want_alphas=True, want_z_samps=True, want_rgb_samps=True)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_render_matches_reference_fixture(name):
+    g = load_golden(name)
+    wl = pu.workload_from_golden(g)
+    _, _, got = pu.cuda_render(wl, state_dict=g.sd, **ALL)
+    stats = pu.compare_render(wl, got, g.out, label=name)
+    print(name, stats)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_point_query_matches_reference_fixture(name):
+    g = load_golden(name)
+    wl = pu.workload_from_golden(g)
+    net, _ = syn.build_model(wl, "cuda", state_dict=g.sd)
+    with torch.no_grad():
+        net.encode(wl.images.cuda(), wl.Ks.cuda(), wl.poses_c2w.cuda(), ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
+        pts = g.query["pts"].cuda()
+        rgb, inv, sig = (t.cpu() for t in net(pts))
+        d_rgb, d_inv, d_sig = (t.cpu() for t in net(pts, only_density=True))
+    assert rgb.shape == g.query["q_rgb"].shape and inv.shape == g.query["q_invalid"].shape and sig.shape == g.query["q_sigma"].shape
+    assert d_rgb.shape == g.query["d_rgb"].shape and d_inv.shape == g.query["d_invalid"].shape
+    same = (inv == g.query["q_invalid"]).all(-1)
+    assert same.float().mean().item() >= 0.98
+    assert torch.allclose(sig[same], g.query["q_sigma"][same], rtol=1e-4, atol=1e-5)
+    assert (rgb[same] - g.query["q_rgb"][same]).abs().max().item() <= 1e-5
+    assert d_rgb.abs().max().item() == 0
+    assert torch.allclose(d_sig[same], g.query["d_sigma"][same], rtol=1e-4, atol=1e-5)
+    assert torch.equal(d_sig, sig)
+
+
+def _full_size_case(wl, wants, lin_out_bias):
+    sd_net, _ = syn.build_model(wl, "cpu")
+    sd = {k: v.clone() for k, v in sd_net.state_dict().items() if not k.startswith("encoder.")}
+    _, _, got = pu.cuda_render(wl, state_dict=sd, **wants)
+    ref = pu.oracle_render(wl, sd, **wants)
+    return pu.compare_render(wl, got, ref, label=wl.name)
+
+
+def test_cfg2_full_frame_vs_oracle():
+    """BASELINE config 2 at its full size (192x640, K=64, one view of rays), evaluator outputs (weights, alphas)."""
+    wl = syn.cfg2_kitti360_eval(stereo=False, lin_out_bias=-4.0, seed=11)
+    stats = _full_size_case(wl, dict(want_weights=True, want_alphas=True), -4.0)
+    print(stats)
+
+
+def test_cfg2_stereo_rays_vs_oracle():
+    wl = syn.cfg2_kitti360_eval(H=96, W=320, stereo=True, lin_out_bias=0.0, seed=12)
+    print(_full_size_case(wl, dict(want_weights=True, want_alphas=True, want_z_samps=True), 0.0))
+
+
+def test_cfg3_training_outputs_vs_oracle():
+    wl = syn.cfg3_kitti_raw_train(H=92, W=306, n=2, lin_out_bias=-4.0, seed=13, ray_subsample=8192)
+    print(_full_size_case(wl, ALL, -4.0))
+
+
+def test_cfg4_re10k_vs_oracle():
+    wl = syn.cfg4_re10k_nvs(H=128, W=192, K=128, lin_out_bias=-4.0, seed=14, ray_subsample=8192)
+    print(_full_size_case(wl, ALL, -4.0))
+
+
+def test_stress_width128_K256_vs_oracle():
+    """BASELINE config 5 shape (Hd=128, K=256) on a ray subset."""
+    wl = syn.cfg2_kitti360_eval(H=48, W=160, K=256, stereo=True, learn_empty=False, lin_out_bias=-4.0, seed=15, ray_subsample=2048)
+    wl.model_conf["mlp_coarse"]["d_hidden"] = 128
+    print(_full_size_case(wl, dict(want_weights=True), -4.0))
+
+
+def test_ragged_K_and_empty_rays():
+    wl = syn.cfg2_kitti360_eval(H=16, W=48, K=48, stereo=True, lin_out_bias=-3.0, seed=16, ray_subsample=77)
+    print(_full_size_case(wl, ALL, -3.0))
+    wl.renderer_conf["n_coarse"] = 5
+    wl.u = wl.u[:, :5].contiguous()
+    print(_full_size_case(wl, ALL, -3.0))
+    net, wrapped = syn.build_model(wl, "cuda")
+    rgb, depth = wrapped(torch.zeros((0, 10, 8), device="cuda"))          # nerf.py:20-24
+    assert rgb.shape == (0, 3) and depth.shape == (0,)
+
+
+def test_size_independent_properties_full_size():
+    """Properties that hold at any size (checked at BASELINE config 2 with the stereo view = 245 760 rays, in-kernel
+    jitter): alpha in [0,1], weights sum to 1 under hard_alpha_cap, depth within [near, far], sorted samples,
+    0/1 flags, determinism for a fixed seed, colour linearity (rgb scales with the images)."""
+    wl = syn.cfg2_kitti360_eval(stereo=True, lin_out_bias=-4.0, seed=21)
+    net, wrapped = syn.build_model(wl, "cuda")
+    dev = "cuda"
+    with torch.no_grad():
+        net.encode(wl.images.to(dev), wl.Ks.to(dev), wl.poses_c2w.to(dev), ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
+        rays = wl.rays.to(dev)
+        torch.manual_seed(5)
+        a = wrapped(rays, want_weights=True, want_alphas=True, want_z_samps=True)["coarse"]
+        torch.manual_seed(5)
+        b = wrapped(rays, want_weights=True, want_alphas=True, want_z_samps=True)["coarse"]
+        c = wrapped(rays, want_z_samps=True)["coarse"]
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    assert not torch.equal(a["z_samps"], c["z_samps"])        # a new call draws new jitter
+    z = a["z_samps"]
+    assert (z[..., 1:] > z[..., :-1]).all() and (z >= 3.0 - 1e-4).all() and (z <= 80.0 + 1e-3).all()
+    assert ((a["alphas"] >= 0) & (a["alphas"] <= 1)).all()
+    assert (a["weights"] >= 0).all()
+    assert (a["weights"].sum(-1) - 1).abs().max().item() <= 2e-5
+    assert ((a["depth"] >= 3.0 - 1e-3) & (a["depth"] <= 80.0 + 1e-2)).all()
+    inv = a["invalid"]
+    assert ((inv == 0) | (inv == 1)).all()
+    assert (a["rgb"] >= -1e-6).all() and (a["rgb"] <= 1 + 1e-5).all()
+    # the bin structure of stratified sampling: sample k lies in disparity bin k
+    disp = 1 / z
+    lo, hi = 1 / 80.0, 1 / 3.0
+    s = (hi - disp) / (hi - lo) * 64
+    kk = torch.arange(64, device=dev).view(1, 1, -1)
+    assert ((s >= kk - 1e-3) & (s <= kk + 1 + 1e-3)).all()
+    # linearity in the colour images: halving the images halves rgb (same jitter)
+    with torch.no_grad():
+        net.encode(wl.images.to(dev), wl.Ks.to(dev), wl.poses_c2w.to(dev), ids_encoder=wl.ids_encoder,
+                   ids_render=wl.ids_render, images_alt=(wl.images.to(dev) * 0.5 + 0.5) * 0.5)
+        torch.manual_seed(5)
+        h = wrapped(rays)["coarse"]
+    assert torch.allclose(h["rgb"], a["rgb"] * 0.5, atol=2e-6)
+    assert torch.equal(h["depth"], a["depth"])
+
+
+def test_errors_are_loud():
+    wl = syn.cfg2_kitti360_eval(H=16, W=48, ray_subsample=32)
+    net, wrapped = syn.build_model(wl, "cuda")
+    with pytest.raises(RuntimeError):
+        wrapped(wl.rays.cuda())                                  # encode() not called
+    net.encode(wl.images.cuda(), wl.Ks.cuda(), wl.poses_c2w.cuda(), ids_encoder=[0], ids_render=[0])
+    with pytest.raises(_lib.BtsCudaError):
+        wrapped(wl.rays)                                         # CPU rays: no CPU fallback
+    wrapped.renderer.n_fine = 16
+    with pytest.raises(NotImplementedError):
+        wrapped(wl.rays.cuda())
+    wrapped.renderer.n_fine = 0
+    with pytest.raises(NotImplementedError):
+        net.encode(wl.images.cuda(), wl.Ks.cuda(), wl.poses_c2w.cuda(), ids_encoder=[0, 1], ids_render=[0])
+        wrapped(wl.rays.cuda())

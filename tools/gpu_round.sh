@@ -1,0 +1,21 @@
+#!/bin/bash
+# One gpurun batch: GPU parity tests, smoke, bench, ncu launch list + one full capture of the render kernel.
+# usage: gpurun --timeout 1500 -- 'bash tools/gpu_round.sh [tag]'
+TAG=${1:-r01}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > $OUT/gpu.txt 2>&1
+nproc > $OUT/host_cores.txt
+echo "== pytest -m gpu" ; timeout 900 python -m pytest tests -x -q -m gpu -s 2>&1 | tail -40 | tee $OUT/pytest_gpu.log
+echo "== smoke" ; timeout 300 python __graft_entry__.py smoke 2>&1 | tail -5 | tee $OUT/smoke.log
+echo "== bench" ; timeout 600 python bench.py --steps 20 --warmup 5 2>&1 | tail -3 | tee $OUT/bench.log
+echo "== bench reference arm" ; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -2 | tee $OUT/bench_ref.log
+if [ -z "$SKIP_NCU" ]; then
+echo "== ncu launch list"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_launch_bench.log 2>&1
+echo "== ncu full capture (render kernel)"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:render_ -s 3 -c 1 -f -o $OUT/render_full \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_bench.log 2>&1
+ls -la $OUT
+fi
