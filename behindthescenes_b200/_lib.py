@@ -48,7 +48,7 @@ EXPORTS = {
     "bts_last_error": (C.c_char_p, []),
     "bts_last_kernel": (C.c_char_p, []),
     "bts_fold_features": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
-                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bts_pack_images": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "bts_render_fwd": (C.c_int, [C.POINTER(BtsScene), C.POINTER(BtsMlp), C.POINTER(BtsRenderCfg), C.c_void_p,
                                  C.c_int64, C.c_int64, C.c_void_p, C.c_uint64, C.POINTER(BtsRenderOut), C.c_void_p]),

@@ -201,7 +201,8 @@ class BTSNet(nn.Module):
         self._require_cuda(feats)
         w_in = self.mlp_coarse.lin_in.weight
         ef = self.empty_feature if self.learn_empty else None
-        key = (self._encode_gen, self._scale, w_in._version, w_in.data_ptr(), feats._version, feats.data_ptr(),
+        b_p = self.mlp_coarse.lin_in.bias
+        key = (self._encode_gen, self._scale, w_in._version, w_in.data_ptr(), b_p._version, feats._version, feats.data_ptr(),
                None if ef is None else (ef._version, ef.data_ptr()))
         hit = self._scene_cache.get("scene")
         if hit is not None and hit[0] == key:
@@ -211,10 +212,11 @@ class BTSNet(nn.Module):
         Hd = self.mlp_coarse.d_hidden
         f = _dev_f32(feats.detach()).view(n, Cf, H, W)
         w = _dev_f32(w_in.detach())
+        b_in = _dev_f32(self.mlp_coarse.lin_in.bias.detach())
         G = torch.empty((n, H, W, Hd), device=dev, dtype=torch.float32)
         g_empty = torch.empty((Hd,), device=dev, dtype=torch.float32) if ef is not None else None
         efd = _dev_f32(ef.detach()) if ef is not None else None
-        rc = lib.bts_fold_features(f.data_ptr(), n, Cf, H, W, w.data_ptr(), w.shape[1], Hd,
+        rc = lib.bts_fold_features(f.data_ptr(), n, Cf, H, W, w.data_ptr(), w.shape[1], b_in.data_ptr(), Hd,
                                    None if efd is None else efd.data_ptr(), G.data_ptr(),
                                    None if g_empty is None else g_empty.data_ptr(), stream)
         _lib.check(rc, "bts_fold_features")
@@ -234,7 +236,7 @@ class BTSNet(nn.Module):
         s.K_f, s.w2c_f = Kf.data_ptr(), Mf.data_ptr()
         s.Vc, s.Cc, s.Hc, s.Wc = Vc, Cc, Hc, Wc
         s.img4, s.K_c, s.w2c_c = img4.data_ptr(), Kc.data_ptr(), Mc.data_ptr()
-        keep = [f, w, G, g_empty, efd, imgs, img4, Kf, Mf, Kc, Mc]
+        keep = [f, w, b_in, G, g_empty, efd, imgs, img4, Kf, Mf, Kc, Mc]
         self._scene_cache["scene"] = (key, s, keep)
         return s, keep
 

@@ -8,7 +8,7 @@
 namespace bts {
 cudaError_t launch_general(const KernelParams& p, bool points, cudaStream_t stream);
 size_t general_smem_bytes(int Hd, int p_pad, int n_blocks);
-cudaError_t launch_fold(const float* feat, int n, int C, int H, int W, const float* w_in, int ld, int Hd,
+cudaError_t launch_fold(const float* feat, int n, int C, int H, int W, const float* w_in, int ld, const float* b_in, int Hd,
                         const float* empty, float* G, float* g_empty, cudaStream_t stream);
 cudaError_t launch_pack_images(const float* img, int nv_total, int Cc, int Hc, int Wc, float* out, cudaStream_t stream);
 }  // namespace bts
@@ -55,12 +55,12 @@ const char* bts_last_error(void) { return g_err; }
 const char* bts_last_kernel(void) { return g_kernel; }
 
 int bts_fold_features(const float* feat_nchw, int32_t n, int32_t C, int32_t H, int32_t W, const float* w_in,
-                      int32_t ld_w_in, int32_t Hd, const float* empty_feature_or_null, float* G_out,
+                      int32_t ld_w_in, const float* b_in, int32_t Hd, const float* empty_feature_or_null, float* G_out,
                       float* g_empty_out_or_null, bts_stream_t stream) {
-  if (!feat_nchw || !w_in || !G_out) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_fold_features: null pointer");
+  if (!feat_nchw || !w_in || !b_in || !G_out) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_fold_features: null pointer");
   if (n < 1 || C < 1 || H < 1 || W < 1 || ld_w_in < C) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_fold_features: bad sizes");
   if (Hd % 32 != 0 || Hd < 32 || Hd > 128) return fail(BTS_ERR_UNSUPPORTED, "d_hidden=%d must be 32/64/96/128", Hd);
-  const cudaError_t e = bts::launch_fold(feat_nchw, n, C, H, W, w_in, ld_w_in, Hd, empty_feature_or_null, G_out,
+  const cudaError_t e = bts::launch_fold(feat_nchw, n, C, H, W, w_in, ld_w_in, b_in, Hd, empty_feature_or_null, G_out,
                                          g_empty_out_or_null, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_fold_features: %s", cudaGetErrorString(e));
   return BTS_OK;

@@ -1,5 +1,5 @@
 // Encode-side glue kernels (run once per encode()/weight update, not per ray):
-//   fold_features : G[b, p, :] = W_in[:, :C] * F[b, :, p]   -- layer-1 linearity: bilinear
+//   fold_features : G[b, p, :] = W_in[:, :C] * F[b, :, p] + b_in   -- layer-1 linearity: bilinear
 //                   interpolation commutes with the feature part of lin_in, so the render kernels interpolate the
 //                   Hd-channel map G instead of the C-channel map F and only contract the 39-wide positional code
 //                   per sample.  fp32, k-sequential FMA accumulation.
@@ -15,7 +15,7 @@ constexpr int kFoldCk = 32;     // channels per shared-memory stage
 
 template <int UN>  // units per thread; Hd = 8 * UN
 __global__ void __launch_bounds__(256) fold_features_kernel(const float* __restrict__ feat, int C, int64_t HW,
-                                                            const float* __restrict__ w_in, int ld, float* __restrict__ G) {
+                                                            const float* __restrict__ w_in, int ld, const float* __restrict__ b_in, float* __restrict__ G) {
   constexpr int Hd = 8 * UN;
   __shared__ __align__(16) float Fs[kFoldCk][kFoldPix];
   __shared__ __align__(16) float Ws[kFoldCk][Hd];
@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) fold_features_kernel(const float* __restr
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int n = 0; n < UN; ++n) acc[i][n] = 0.0f;
+    for (int n = 0; n < UN; ++n) acc[i][n] = __ldg(b_in + tn * UN + n);   // lin_in bias rides along (resnetfc.py:147)
   const float* fb = feat + (size_t)b * C * HW;
   for (int c0 = 0; c0 < C; c0 += kFoldCk) {
     for (int i = threadIdx.x; i < kFoldCk * kFoldPix; i += 256) {
@@ -68,10 +68,10 @@ __global__ void __launch_bounds__(256) fold_features_kernel(const float* __restr
 }
 
 __global__ void fold_empty_kernel(const float* __restrict__ empty, int C, const float* __restrict__ w_in, int ld, int Hd,
-                                  float* __restrict__ g_empty) {
+                                  const float* __restrict__ b_in, float* __restrict__ g_empty) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= Hd) return;
-  float a = 0.0f;
+  float a = __ldg(b_in + n);
   for (int c = 0; c < C; ++c) a = fmaf(__ldg(w_in + (size_t)n * ld + c), __ldg(empty + c), a);
   g_empty[n] = a;
 }
@@ -89,21 +89,21 @@ __global__ void pack_images_kernel(const float* __restrict__ img, int Cc, int64_
   out[i] = o;
 }
 
-cudaError_t launch_fold(const float* feat, int n, int C, int H, int W, const float* w_in, int ld, int Hd,
+cudaError_t launch_fold(const float* feat, int n, int C, int H, int W, const float* w_in, int ld, const float* b_in, int Hd,
                         const float* empty, float* G, float* g_empty, cudaStream_t stream) {
   const int64_t HW = (int64_t)H * W;
   dim3 grid((unsigned)((HW + kFoldPix - 1) / kFoldPix), (unsigned)n);
   switch (Hd / 8) {
-    case 4: fold_features_kernel<4><<<grid, 256, 0, stream>>>(feat, C, HW, w_in, ld, G); break;
-    case 8: fold_features_kernel<8><<<grid, 256, 0, stream>>>(feat, C, HW, w_in, ld, G); break;
-    case 12: fold_features_kernel<12><<<grid, 256, 0, stream>>>(feat, C, HW, w_in, ld, G); break;
-    case 16: fold_features_kernel<16><<<grid, 256, 0, stream>>>(feat, C, HW, w_in, ld, G); break;
+    case 4: fold_features_kernel<4><<<grid, 256, 0, stream>>>(feat, C, HW, w_in, ld, b_in, G); break;
+    case 8: fold_features_kernel<8><<<grid, 256, 0, stream>>>(feat, C, HW, w_in, ld, b_in, G); break;
+    case 12: fold_features_kernel<12><<<grid, 256, 0, stream>>>(feat, C, HW, w_in, ld, b_in, G); break;
+    case 16: fold_features_kernel<16><<<grid, 256, 0, stream>>>(feat, C, HW, w_in, ld, b_in, G); break;
     default: return cudaErrorInvalidValue;
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (empty && g_empty) {
-    fold_empty_kernel<<<(Hd + 127) / 128, 128, 0, stream>>>(empty, C, w_in, ld, Hd, g_empty);
+    fold_empty_kernel<<<(Hd + 127) / 128, 128, 0, stream>>>(empty, C, w_in, ld, Hd, b_in, g_empty);
     e = cudaGetLastError();
   }
   return e;

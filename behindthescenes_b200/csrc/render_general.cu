@@ -3,7 +3,7 @@
 // One warp renders one ray at a time (grid-stride).  A ray's K samples are processed in chunks of 32:
 //   A  lane = sample : stratified depth, world point, projection into the encoder view, depth code, positional code
 //                      (written to per-warp shared memory, sample-minor), bilinear tap set (shared memory)
-//   B  lane = hidden units (NU = Hd/32 per lane): for 8 samples at a time, h = b_in + bilinear(G) + W_pe * code,
+//   B  lane = hidden units (NU = Hd/32 per lane): for 8 samples at a time, h = bilinear(G) + W_pe * code  (G carries the lin_in bias),
 //      ResnetFC blocks, sigma logit = w_out . relu(h) + b_out  (warp reduction), handed back to lane = sample
 //   C  lane = sample : alpha, transmittance scan (warp scan + carry across chunks), weights, depth
 //   D  lane = sample : per colour view projection + bilinear RGB fetch, invalid flags, weighted colour reduction
@@ -12,6 +12,7 @@
 // Reference arithmetic: models/common/render/nerf.py:103-123 (sampling), :210-313 (composite);
 // models/bts/model/models_bts.py:138-338 (field); models/common/model/resnetfc.py:53-62,132-184 (MLP).
 #include "common.cuh"
+#include "render_phases.cuh"
 
 namespace bts {
 
@@ -47,7 +48,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) render_general_kernel(const
   const int P = p.mlp.P, Ppad = p.p_pad, nb = p.mlp.n_blocks;
   const GeneralSmemLayout L = general_layout(Hd, Ppad, nb);
   float* s_wpe = smem + L.wpe;      // [Ppad][Hd]  (W_in[:, C + j] transposed; rows >= P are zero)
-  float* s_bin = smem + L.b_in;
   float* s_wout = smem + L.w_out;
   float* s_blk = smem + L.blocks;   // per block: fc0^T [Hd][Hd], b0 [Hd], fc1^T [Hd][Hd], b1 [Hd]
   float* w_pe = smem + L.per_warp + warp * L.warp_floats + L.warp_pe;     // [Ppad][32]
@@ -62,7 +62,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) render_general_kernel(const
       s_wpe[i] = j < P ? __ldg(p.mlp.w_in + (size_t)n * ld + p.mlp.C + j) : 0.0f;
     }
     for (int i = threadIdx.x; i < Hd; i += blockDim.x) {
-      s_bin[i] = __ldg(p.mlp.b_in + i);
       s_wout[i] = __ldg(p.mlp.w_out + i);
     }
     for (int b = 0; b < nb; ++b) {
@@ -199,7 +198,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) render_general_kernel(const
             for (int n = 0; n < NU; ++n) g[n] = 0.0f;
           }
 #pragma unroll
-          for (int n = 0; n < NU; ++n) acc[ss][n] = s_bin[lane * NU + n] + g[n];
+          for (int n = 0; n < NU; ++n) acc[ss][n] = g[n];   // lin_in bias is already inside G / g_empty
         }
         // positional-code part of lin_in: acc += W_pe[:, j] * code[j]
         for (int j = 0; j < P; ++j) {
@@ -281,87 +280,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) render_general_kernel(const
       // ---- phase C: alpha compositing (nerf.py:283-299) ----
       float wgt = 0.0f;
       if (!kPoints) {
-        const float delta = (k + 1 < K) ? __fsub_rn(z_next, z) : 1e10f;            // :225-228
-        float alpha = __fsub_rn(1.0f, expf(-(fabsf(delta) * fmaxf(sigma, 0.0f))));  // :283
-        if (cfg.hard_alpha_cap && k == K - 1) alpha = 1.0f;                         // :285-286
-        float tr = valid ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;        // :290-292
-        float incl = tr;                                                            // inclusive product scan
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const float up = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl *= up;
-        }
-        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-        if (lane == 0) excl = 1.0f;
-        const float Tk = T_carry * excl;
-        T_carry *= __shfl_sync(0xffffffffu, incl, 31);
-        wgt = valid ? alpha * Tk : 0.0f;                                            // :294
-        depth_part = fmaf(wgt, z, depth_part);                                      // :299
-        wsum_part += wgt;
-        if (valid) {
-          if (p.out.weights) p.out.weights[sample_id] = wgt;
-          if (p.out.alphas) p.out.alphas[sample_id] = alpha;
-          if (p.out.z_samps) p.out.z_samps[sample_id] = z;
-        }
+        wgt = composite_chunk(p, lane, k, K, valid, z, z_next, sigma, sample_id, T_carry, depth_part, wsum_part);
       } else if (valid) {
         p.q_sigma[sample_id] = sigma;
         p.q_invalid_f[sample_id] = inv_f ? 1.0f : 0.0f;
       }
 
       // ---- phase D: colour views (models_bts.py:218-264, :330-334) ----
-      const bool want_color = kPoints ? (p.q_rgb != nullptr || p.q_invalid != nullptr)
-                                      : (p.out.rgb != nullptr || p.out.invalid != nullptr || p.out.rgb_samps != nullptr);
-      if (want_color) {
-        for (int v = 0; v < Vc; ++v) {
-          View vc;
-          load_view(vc, p.scene.K_c + (bl * Vc + v) * 9, p.scene.w2c_c + (bl * Vc + v) * 16);
-          const Proj pc = project(vc, X, Y, Z);
-          const Taps t = bilinear_taps(pc.u, pc.v, Hc, Wc);
-          const float4* base = reinterpret_cast<const float4*>(p.scene.img4) + ((bl * Vc + v) * Hc + t.y0) * (int64_t)Wc + t.x0;
-          float col[4] = {0, 0, 0, 0};
-          if (valid) {
-            const float4 c00 = __ldg(base), c01 = __ldg(base + t.dx);
-            const float4 c10 = __ldg(base + t.dy * Wc), c11 = __ldg(base + t.dy * Wc + t.dx);
-            const float w00 = t.wx0 * t.wy0, w01 = t.wx1 * t.wy0, w10 = t.wx0 * t.wy1, w11 = t.wx1 * t.wy1;
-            col[0] = fmaf(c11.x, w11, fmaf(c10.x, w10, fmaf(c01.x, w01, c00.x * w00)));
-            col[1] = fmaf(c11.y, w11, fmaf(c10.y, w10, fmaf(c01.y, w01, c00.y * w00)));
-            col[2] = fmaf(c11.z, w11, fmaf(c10.z, w10, fmaf(c01.z, w01, c00.z * w00)));
-            col[3] = fmaf(c11.w, w11, fmaf(c10.w, w10, fmaf(c01.w, w01, c00.w * w00)));
-          }
-          const float inv = (pc.invalid | inv_f) ? 1.0f : 0.0f;   // :333-334
-          if (!kPoints) {
-            if (valid) {
-              if (p.out.invalid) p.out.invalid[sample_id * Vc + v] = inv;
-              if (p.out.rgb_samps)
-                for (int c = 0; c < Cc; ++c) p.out.rgb_samps[(sample_id * Vc + v) * Cc + c] = col[c];
-            }
-            if (p.out.rgb) {
-              for (int c = 0; c < Cc; ++c) {
-                const float tot = warp_sum(wgt * col[c]);   // nerf.py:298
-                if (lane == 0) w_rgb[v * 4 + c] += tot;
-              }
-            }
-          } else if (valid) {
-            if (p.q_invalid) p.q_invalid[sample_id * Vc + v] = inv;
-            if (p.q_rgb)
-              for (int c = 0; c < Cc; ++c) p.q_rgb[(sample_id * Vc + v) * Cc + c] = col[c];
-          }
-        }
-      }
+      colour_views<kPoints>(p, lane, bl, X, Y, Z, valid, inv_f, wgt, sample_id, w_rgb);
       __syncwarp();
     }  // chunks
 
-    if (!kPoints) {
-      const float depth = warp_sum(depth_part);
-      const float wsum = warp_sum(wsum_part);
-      if (lane == 0 && p.out.depth) p.out.depth[item] = depth;
-      if (p.out.rgb && lane < Vc * Cc) {
-        float r = w_rgb[(lane / Cc) * 4 + (lane % Cc)];
-        if (cfg.white_bkgd) r = r + 1.0f - wsum;   // nerf.py:301-304
-        p.out.rgb[item * Vc * Cc + lane] = r;
-      }
-      __syncwarp();
-    }
+    if (!kPoints) finish_ray(p, lane, item, depth_part, wsum_part, w_rgb);
   }
 }
 

@@ -63,7 +63,6 @@ def weights_state_dict(wl):
 def cpu_reference_run(wl, sd, n_rays, steps, warmup):
     from oracle import bts_oracle as orc
     from tests.golden_io import mlp_params
-    torch.set_num_threads(os.cpu_count() or 1)
     st = orc.encode_state(wl.images, wl.Ks, wl.poses_c2w, wl.feats, wl.ids_encoder, wl.ids_render)
     fcfg = orc.FieldConfig.from_model_conf(wl.model_conf)
     rcfg = orc.RenderConfig.from_renderer_conf(wl.renderer_conf)
@@ -72,6 +71,24 @@ def cpu_reference_run(wl, sd, n_rays, steps, warmup):
     mlp = mlp_params(sd)
     out = None
     times = []
+    # "all the host threads it can use": torch's intra-op pool at the core count this process may run on, unless a
+    # smaller pool is faster for this op chain (many small elementwise ops) -- probe a few sizes on a 2048-ray sample.
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:
+        avail = os.cpu_count() or 1
+    best = (None, float("inf"))
+    with torch.no_grad():
+        for t in sorted({min(avail, c) for c in (8, 16, 32, 64, avail)}):
+            torch.set_num_threads(t)
+            r2, u2 = rays[:, :2048].contiguous(), u[:2048].contiguous()
+            orc.render(st, mlp, fcfg, rcfg, r2, u=u2, empty_feature=sd.get("empty_feature"))
+            t0 = time.perf_counter()
+            orc.render(st, mlp, fcfg, rcfg, r2, u=u2, empty_feature=sd.get("empty_feature"))
+            dt = time.perf_counter() - t0
+            if dt < best[1]:
+                best = (t, dt)
+    torch.set_num_threads(best[0])
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()

@@ -10,8 +10,8 @@
  * of the calling thread is available from bts_last_error().
  *
  * Data layout in HBM (what "encode" leaves resident for the render kernels):
- *   G      (n, H, W, Hd)      "folded feature map": G[p] = W_in[:, :C] * F[:, p]   (bts_fold_features)
- *   g_empty(Hd)               W_in[:, :C] * empty_feature                            (learn_empty)
+ *   G      (n, H, W, Hd)      "folded feature map": G[p] = W_in[:, :C] * F[:, p] + b_in   (bts_fold_features)
+ *   g_empty(Hd)               W_in[:, :C] * empty_feature + b_in                      (learn_empty)
  *   img4   (n, Vc, Hc, Wc, 4) colour views, channels-last padded to 4                (bts_pack_images)
  *   K_*    (n, V, 3, 3), w2c_* (n, V, 4, 4) row-major camera matrices as the reference caches them
  */
@@ -109,10 +109,11 @@ int bts_abi_version(void);
 const char* bts_last_error(void);
 
 /* Encode-side glue, once per encode() / weight update (SURVEY.md §7 "layer-1 linearity"):
- *   G[b, y, x, :] = w_in[:, :C] * feat[b, :, y, x];   g_empty = w_in[:, :C] * empty_feature  (if non-NULL).
+ *   G[b, y, x, :] = w_in[:, :C] * feat[b, :, y, x] + b_in;   g_empty = w_in[:, :C] * empty_feature + b_in  (if non-NULL).
+ * The lin_in bias is folded in here, so the render kernels never read mlp.b_in.
  * feat is the encoder output exactly as BTSNet.encode caches it: (n, C, H, W) NCHW (models_bts.py:126-128). */
 int bts_fold_features(const float* feat_nchw, int32_t n, int32_t C, int32_t H, int32_t W, const float* w_in,
-                      int32_t ld_w_in, int32_t Hd, const float* empty_feature_or_null, float* G_out,
+                      int32_t ld_w_in, const float* b_in, int32_t Hd, const float* empty_feature_or_null, float* G_out,
                       float* g_empty_out_or_null, bts_stream_t stream);
 
 /* (n, Vc, Cc, Hc, Wc) NCHW colour views (grid_c_imgs, models_bts.py:133) -> (n, Vc, Hc, Wc, 4) channels-last. */

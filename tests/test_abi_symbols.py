@@ -51,7 +51,7 @@ def test_struct_mirrors_match_header_layout():
 def test_argument_validation_without_gpu(lib):
     """Validation paths return before any CUDA call, so they can be exercised on the CPU box."""
     from behindthescenes_b200 import _lib
-    assert lib.bts_fold_features(None, 1, 64, 4, 4, None, 103, 64, None, None, None, None) == -1
+    assert lib.bts_fold_features(None, 1, 64, 4, 4, None, 103, None, 64, None, None, None, None) == -1
     assert b"null" in lib.bts_last_error()
     rc = lib.bts_render_fwd(None, None, None, None, 1, 1, None, 0, None, None)
     assert rc == -1

@@ -146,6 +146,10 @@ def test_errors_are_loud():
     with pytest.raises(NotImplementedError):
         wrapped(wl.rays.cuda())
     wrapped.renderer.n_fine = 0
+    # several encoder views: the features stand-in must return one map per encoder view
+    wl2 = syn.cfg2_kitti360_eval(H=16, W=48, ray_subsample=32)
+    wl2.feats = torch.cat((wl2.feats, wl2.feats), 0)
+    net2, wrapped2 = syn.build_model(wl2, "cuda")
+    net2.encode(wl2.images.cuda(), wl2.Ks.cuda(), wl2.poses_c2w.cuda(), ids_encoder=[0, 1], ids_render=[0])
     with pytest.raises(NotImplementedError):
-        net.encode(wl.images.cuda(), wl.Ks.cuda(), wl.poses_c2w.cuda(), ids_encoder=[0, 1], ids_render=[0])
-        wrapped(wl.rays.cuda())
+        wrapped2(wl2.rays.cuda())
