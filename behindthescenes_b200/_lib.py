@@ -47,6 +47,7 @@ EXPORTS = {
     "bts_abi_version": (C.c_int, []),
     "bts_last_error": (C.c_char_p, []),
     "bts_last_kernel": (C.c_char_p, []),
+    "bts_debug_tc_timeouts": (C.c_int, []),
     "bts_fold_features": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bts_pack_images": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),

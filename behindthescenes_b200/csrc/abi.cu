@@ -10,6 +10,9 @@ cudaError_t launch_general(const KernelParams& p, bool points, cudaStream_t stre
 size_t general_smem_bytes(int Hd, int p_pad, int n_blocks);
 cudaError_t launch_fold(const float* feat, int n, int C, int H, int W, const float* w_in, int ld, const float* b_in, int Hd,
                         const float* empty, float* G, float* g_empty, cudaStream_t stream);
+bool tc_supported(const KernelParams& p);
+cudaError_t launch_tc(const KernelParams& p, cudaStream_t stream);
+int tc_barrier_timeouts();
 cudaError_t launch_pack_images(const float* img, int nv_total, int Cc, int Hc, int Wc, float* out, cudaStream_t stream);
 }  // namespace bts
 
@@ -53,6 +56,7 @@ extern "C" {
 int bts_abi_version(void) { return BTS_ABI_VERSION; }
 const char* bts_last_error(void) { return g_err; }
 const char* bts_last_kernel(void) { return g_kernel; }
+int bts_debug_tc_timeouts(void) { return bts::tc_barrier_timeouts(); }
 
 int bts_fold_features(const float* feat_nchw, int32_t n, int32_t C, int32_t H, int32_t W, const float* w_in,
                       int32_t ld_w_in, const float* b_in, int32_t Hd, const float* empty_feature_or_null, float* G_out,
@@ -90,8 +94,15 @@ int bts_render_fwd(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg*
   p.scene = *scene; p.mlp = *mlp; p.cfg = *cfg; p.out = *out;
   p.rays = rays; p.u = u_or_null; p.n_items = n * R; p.per_batch = R; p.seed = seed;
   p.p_pad = (mlp->P + 3) & ~3;
-  g_kernel = "general";
-  const cudaError_t e = bts::launch_general(p, false, reinterpret_cast<cudaStream_t>(stream));
+  cudaError_t e;
+  if (cfg->precision != 2 && bts::tc_supported(p)) {
+    g_kernel = "tc";
+    e = bts::launch_tc(p, reinterpret_cast<cudaStream_t>(stream));
+  } else {
+    if (cfg->precision == 1) return fail(BTS_ERR_UNSUPPORTED, "fast tier needs the tensor-core kernel (Hd=64, n_blocks=0, 6-octave code, K%%32==0)");
+    g_kernel = "general";
+    e = bts::launch_general(p, false, reinterpret_cast<cudaStream_t>(stream));
+  }
   if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_render_fwd: %s", cudaGetErrorString(e));
   return BTS_OK;
 }

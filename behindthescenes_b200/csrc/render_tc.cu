@@ -1,0 +1,357 @@
+// Tensor-core render kernel for the flagship BTS configuration (d_hidden = 64, n_blocks = 0, 6-octave code with
+// include_input, K a multiple of 32): the positional-code part of lin_in runs on the 5th-gen tensor cores
+// (tcgen05.mma, accumulator in TMEM), everything else on the CUDA cores, all fused per ray.
+//
+// CTA = 4 warps; each warp owns one ray per pass; a pass is processed in K/32 sub-tiles of 128 samples
+// (row r of the MMA tile = lane r%32 of warp r/32 = sample 32*j + lane of that warp's ray):
+//   P1  lane = sample : stratified depth, world point, projection into the encoder view, depth code, positional code
+//                       -> A operand written straight into TMEM (tcgen05.st): 36 sin/cos values as fp16 hi + fp16 lo
+//                       (two-term split = fp32-grade products), the 3 raw coordinates as tf32 hi/lo (unbounded range)
+//   MMA one thread    : D[128x64] = A16hi*W16hi + A16lo*W16hi + A16hi*W16lo (kind::f16, K=48)
+//                                   + Araw*WrawA + Araw*WrawB            (kind::tf32, K=8), fp32 accumulate in TMEM
+//   P2  half-warp = sample : coalesced bilinear gather of the folded map G (4 taps x 64 channels = 4 x 256 B per
+//                       sample, one 16-byte load per lane and tap) -> interpolated row in shared memory
+//   P3  lane = sample : h = D (tcgen05.ld) + G-row ; sigma = softplus(w_out . relu(h) + b_out)
+//   C/D lane = sample : alpha compositing scan, colour views (render_phases.cuh)
+// The fast tier (cfg.precision = 1) drops the lo terms (single fp16 / tf32 pass).
+//
+// Reference arithmetic: models/bts/model/models_bts.py:138-216 (sample_features), :266-338 (forward),
+// models/common/model/code.py:30-42, resnetfc.py:132-184 (n_blocks = 0), models/common/render/nerf.py:103-123, :210-313.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "render_phases.cuh"
+#include "tcgen05.cuh"
+
+namespace bts {
+
+__device__ int g_tc_barrier_timeouts = 0;   // bug guard: bounded mbarrier waits that expired (read by tests)
+
+namespace tcr {
+
+constexpr int kThreads = 128;
+constexpr uint32_t kColD = 0, kColAhi = 64, kColAlo = 88, kColAraw = 112, kTmemCols = 128;
+constexpr int kGiStride = 68;   // floats per interpolated row in shared memory (64 + 4: conflict-free both ways)
+
+// shared-memory map (bytes)
+constexpr int kOffW16hi = 0;                    // [6 chunks][64 rows][16 B]  fp16, K-major no-swizzle
+constexpr int kOffW16lo = kOffW16hi + 6 * 64 * 16;
+constexpr int kOffWrawA = kOffW16lo + 6 * 64 * 16;   // [2][64][16 B] tf32: [hi0 hi1 hi2 hi0 | hi1 hi2 0 0]
+constexpr int kOffWrawB = kOffWrawA + 2 * 64 * 16;   //               tf32: [lo0 lo1 lo2 0 | 0 0 0 0]
+constexpr int kOffWout = kOffWrawB + 2 * 64 * 16;    // 64 floats
+constexpr int kOffGempty = kOffWout + 256;           // 64 floats
+constexpr int kOffBar = kOffGempty + 256;            // mbarrier (8 B) + tmem base (4 B) + pad
+constexpr int kOffWarp = kOffBar + 16;
+constexpr int kWarpTaps = 0;                         // [32][8] floats
+constexpr int kWarpGi = 32 * 8 * 4;                  // [32][68] floats
+constexpr int kWarpRgb = kWarpGi + 32 * kGiStride * 4;
+constexpr int kWarpBytes = kWarpRgb + kMaxColorViews * 4 * 4;
+constexpr int kSmemBytes = kOffWarp + 4 * kWarpBytes;
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// (s, c) -> fp16 pair hi and the fp16 pair of the residuals
+__device__ __forceinline__ void split_h2(float s, float c, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(s, c);
+  const float2 hf = __half22float2(h);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = pack_h2(s - hf.x, c - hf.y);
+}
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+template <bool kExact>
+__global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8);
+  float* s_wout = reinterpret_cast<float*>(smem + kOffWout);
+  float* s_gempty = reinterpret_cast<float*>(smem + kOffGempty);
+  unsigned char* wbase = smem + kOffWarp + warp * kWarpBytes;
+  float4* w_taps = reinterpret_cast<float4*>(wbase + kWarpTaps);
+  float* w_gi = reinterpret_cast<float*>(wbase + kWarpGi);
+  float* w_rgb = reinterpret_cast<float*>(wbase + kWarpRgb);
+
+  const BtsRenderCfg& cfg = p.cfg;
+  const int C = p.mlp.C, ld = C + p.mlp.P;
+
+  // ---- one-time setup: weights -> B operands (fp16 hi/lo, tf32 hi/lo), TMEM allocation, mbarrier ----
+  for (int i = tid; i < 64 * 48; i += kThreads) {
+    const int n = i / 48, c = i % 48;
+    float w = 0.0f;
+    if (c < 36) {   // A column c = (d*6 + i)*2 + sc  <->  reference code index 3 + i*6 + sc*3 + d (code.py:39-41)
+      const int sc = c & 1, di = c >> 1, d = di / 6, oct = di % 6;
+      w = __ldg(p.mlp.w_in + (size_t)n * ld + C + 3 + oct * 6 + sc * 3 + d);
+    }
+    const __half hi = __float2half_rn(w);
+    const __half lo = __float2half_rn(w - __half2float(hi));
+    const int off = ((c >> 3) * 64 + n) * 16 + (c & 7) * 2;
+    *reinterpret_cast<__half*>(smem + kOffW16hi + off) = hi;
+    *reinterpret_cast<__half*>(smem + kOffW16lo + off) = lo;
+  }
+  if (tid < 64) {
+    const int n = tid;
+    float hi[3], lo[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float w = __ldg(p.mlp.w_in + (size_t)n * ld + C + d);
+      hi[d] = tf32_hi(w);
+      lo[d] = w - hi[d];
+    }
+    *reinterpret_cast<float4*>(smem + kOffWrawA + (0 * 64 + n) * 16) = make_float4(hi[0], hi[1], hi[2], hi[0]);
+    *reinterpret_cast<float4*>(smem + kOffWrawA + (1 * 64 + n) * 16) = make_float4(hi[1], hi[2], 0.f, 0.f);
+    *reinterpret_cast<float4*>(smem + kOffWrawB + (0 * 64 + n) * 16) = make_float4(lo[0], lo[1], lo[2], 0.f);
+    *reinterpret_cast<float4*>(smem + kOffWrawB + (1 * 64 + n) * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+    s_wout[n] = __ldg(p.mlp.w_out + n);
+    s_gempty[n] = p.scene.g_empty ? __ldg(p.scene.g_empty + n) : 0.0f;
+  }
+  if (warp == 0) tc::tmem_alloc<kTmemCols>(tmem_slot);
+  if (tid == 0) {
+    tc::mbar_init(bar, 1);
+    tc::fence_mbar_init();
+  }
+  tc::fence_proxy_async_smem();          // weight tiles are read by the tensor core through the async proxy
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes
+  uint32_t bar_phase = 0;
+  bool wait_disabled = false;
+
+  const int K = cfg.n_coarse, Vc = p.scene.Vc;
+  const int H = p.scene.H, W = p.scene.W;
+  const float b_out = __ldg(p.mlp.b_out);
+  const bool use_empty = cfg.learn_empty && p.scene.g_empty != nullptr;
+  const uint32_t idesc16 = tc::instr_desc(tc::kFmtF16, 128, 64), idesc32 = tc::instr_desc(tc::kFmtTF32, 128, 64);
+
+  const int64_t n_rays = p.n_items;
+  const int64_t n_pass = (n_rays + 3) / 4;
+  for (int64_t pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
+    const int64_t ray_raw = pass * 4 + warp;
+    const bool active = ray_raw < n_rays;
+    const int64_t ray = active ? ray_raw : n_rays - 1;
+    const int64_t b = ray / p.per_batch;
+    const float rv = lane < 8 ? __ldg(p.rays + ray * 8 + lane) : 0.0f;
+    const float ro0 = __shfl_sync(0xffffffffu, rv, 0), ro1 = __shfl_sync(0xffffffffu, rv, 1), ro2 = __shfl_sync(0xffffffffu, rv, 2);
+    const float rd0 = __shfl_sync(0xffffffffu, rv, 3), rd1 = __shfl_sync(0xffffffffu, rv, 4), rd2 = __shfl_sync(0xffffffffu, rv, 5);
+    const float near_ = __shfl_sync(0xffffffffu, rv, 6), far_ = __shfl_sync(0xffffffffu, rv, 7);
+    float T_carry = 1.0f, depth_part = 0.0f, wsum_part = 0.0f;
+    if (lane < kMaxColorViews * 4) w_rgb[lane] = 0.0f;
+    wait_disabled = wait_disabled || (*reinterpret_cast<volatile int*>(&g_tc_barrier_timeouts) != 0);
+    View vf;
+    load_view(vf, p.scene.K_f + b * 9, p.scene.w2c_f + b * 16);
+
+    for (int c0 = 0; c0 < K; c0 += 32) {
+      const int k = c0 + lane;
+      const int64_t sample_id = ray * K + k;
+      // ---------------- P1: per-sample scalar work, A operand -> TMEM ----------------
+      const float z = sample_depth(p, ray, k, near_, far_);
+      float z_next = __shfl_down_sync(0xffffffffu, z, 1);
+      if (lane == 31 && k + 1 < K) z_next = sample_depth(p, ray, k + 1, near_, far_);
+      const float X = __fadd_rn(ro0, __fmul_rn(z, rd0));   // nerf.py:231
+      const float Y = __fadd_rn(ro1, __fmul_rn(z, rd1));
+      const float Z = __fadd_rn(ro2, __fmul_rn(z, rd2));
+      const Proj pf = project(vf, X, Y, Z);
+      const bool inv_f = pf.invalid;
+      const float pv[3] = {pf.u, pf.v, depth_code(cfg, pf)};
+      {
+        const Taps t = bilinear_taps(pf.u, pf.v, H, W);
+        const int p00 = (int)((b * H + t.y0) * (int64_t)W + t.x0);
+        float4 a, w;
+        a.x = __int_as_float(p00 * 16);                 // in float4 units of a 64-channel pixel
+        a.y = __int_as_float(t.dx * 16);
+        a.z = __int_as_float(t.dy * W * 16);
+        a.w = __int_as_float((use_empty && inv_f) ? 1 : 0);
+        w.x = t.wx0 * t.wy0; w.y = t.wx1 * t.wy0; w.z = t.wx0 * t.wy1; w.w = t.wx1 * t.wy1;
+        w_taps[lane * 2 + 0] = a;
+        w_taps[lane * 2 + 1] = w;
+      }
+      {
+        uint32_t ahi[24], alo[24], araw[8];
+#pragma unroll
+        for (int i = 18; i < 24; ++i) { ahi[i] = 0u; alo[i] = 0u; }
+        const float kHalfPi = 1.57079637050628662109375f;
+        const bool big = fmaxf(fabsf(pv[0]), fmaxf(fabsf(pv[1]), fabsf(pv[2]))) > kPeFastLimit;
+        if (!big) {
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            float s, c;
+            sincosf(__fmul_rn(pv[d], cfg.freq_factor), &s, &c);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+              if (kExact) split_h2(s, c, ahi[d * 6 + i], alo[d * 6 + i]);
+              else ahi[d * 6 + i] = pack_h2(s, c);
+              const float s2 = 2.0f * s * c;
+              c = (c - s) * (c + s);
+              s = s2;
+            }
+          }
+        } else {   // far outside the frustum: evaluate every term on the reference's own rounded argument
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            float f = cfg.freq_factor;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+              const float s = sinf(__fmul_rn(pv[d], f)), c = sinf(fmaf(pv[d], f, kHalfPi));
+              if (kExact) split_h2(s, c, ahi[d * 6 + i], alo[d * 6 + i]);
+              else ahi[d * 6 + i] = pack_h2(s, c);
+              f *= 2.0f;
+            }
+          }
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const float h = tf32_hi(pv[d]);
+          araw[d] = __float_as_uint(h);
+          araw[3 + d] = kExact ? __float_as_uint(pv[d] - h) : 0u;
+        }
+        araw[6] = 0u; araw[7] = 0u;
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          uint32_t v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = ahi[g * 8 + e];
+          tc::tmem_st_x8(t_lane + kColAhi + g * 8, v);
+          if (kExact) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = alo[g * 8 + e];
+            tc::tmem_st_x8(t_lane + kColAlo + g * 8, v);
+          }
+        }
+        tc::tmem_st_x8(t_lane + kColAraw, araw);
+        tc::tmem_st_wait();
+      }
+      tc::tc_fence_before_sync();
+      __syncthreads();                     // all 128 rows of the A tile are in TMEM; D of the previous tile is consumed
+
+      // ---------------- MMA issue (one thread) ----------------
+      if (tid == 0) {
+        tc::tc_fence_after_sync();
+        const uint32_t sW = tc::smem_u32(smem);
+#pragma unroll
+        for (int ks = 0; ks < 3; ++ks) {
+          const uint64_t bhi = tc::smem_desc_kmajor_noswizzle(sW + kOffW16hi + ks * 2 * 64 * 16, 64 * 16, 128);
+          tc::mma_f16_ts(tmem + kColD, tmem + kColAhi + ks * 8, bhi, idesc16, ks > 0);
+          if (kExact) {
+            const uint64_t blo = tc::smem_desc_kmajor_noswizzle(sW + kOffW16lo + ks * 2 * 64 * 16, 64 * 16, 128);
+            tc::mma_f16_ts(tmem + kColD, tmem + kColAlo + ks * 8, bhi, idesc16, 1);
+            tc::mma_f16_ts(tmem + kColD, tmem + kColAhi + ks * 8, blo, idesc16, 1);
+          }
+        }
+        tc::mma_tf32_ts(tmem + kColD, tmem + kColAraw, tc::smem_desc_kmajor_noswizzle(sW + kOffWrawA, 64 * 16, 128), idesc32, 1);
+        if (kExact)
+          tc::mma_tf32_ts(tmem + kColD, tmem + kColAraw, tc::smem_desc_kmajor_noswizzle(sW + kOffWrawB, 64 * 16, 128), idesc32, 1);
+        tc::mma_commit(bar);
+      }
+      __syncwarp();
+
+      // ---------------- P2: coalesced bilinear gather of G, half-warp per sample ----------------
+      {
+        const int hw = lane >> 4, q = lane & 15;
+        const float4* G4 = reinterpret_cast<const float4*>(p.scene.G);
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+          const int s = 2 * i + hw;
+          const float4 a = w_taps[s * 2 + 0];
+          const float4 w = w_taps[s * 2 + 1];
+          float4 g;
+          if (__float_as_int(a.w)) {
+            g = reinterpret_cast<const float4*>(s_gempty)[q];
+          } else {
+            const float4* g00 = G4 + (size_t)(uint32_t)__float_as_int(a.x) + q;
+            const float4* g10 = g00 + __float_as_int(a.z);
+            const float4 v00 = __ldg(g00), v01 = __ldg(g00 + __float_as_int(a.y));
+            const float4 v10 = __ldg(g10), v11 = __ldg(g10 + __float_as_int(a.y));
+            g.x = fmaf(v11.x, w.w, fmaf(v10.x, w.z, fmaf(v01.x, w.y, v00.x * w.x)));
+            g.y = fmaf(v11.y, w.w, fmaf(v10.y, w.z, fmaf(v01.y, w.y, v00.y * w.x)));
+            g.z = fmaf(v11.z, w.w, fmaf(v10.z, w.z, fmaf(v01.z, w.y, v00.z * w.x)));
+            g.w = fmaf(v11.w, w.w, fmaf(v10.w, w.z, fmaf(v01.w, w.y, v00.w * w.x)));
+          }
+          *reinterpret_cast<float4*>(w_gi + s * kGiStride + q * 4) = g;
+        }
+      }
+      __syncwarp();
+
+      // ---------------- P3: accumulator + interpolated row -> sigma ----------------
+      // bounded wait (bug guard): after the first expiry every later wait is skipped so a pipeline bug cannot hang the GPU
+      if (!wait_disabled && !tc::mbar_wait(bar, bar_phase, 1u << 20)) {
+        atomicAdd(&g_tc_barrier_timeouts, 1);
+        wait_disabled = true;
+      }
+      bar_phase ^= 1u;
+      tc::tc_fence_after_sync();
+      float logit = b_out;
+      {
+        uint32_t dv[4][16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tc::tmem_ld_x16(t_lane + kColD + c * 16, dv[c]);
+        tc::tmem_ld_wait();
+        const float4* grow = reinterpret_cast<const float4*>(w_gi + lane * kGiStride);
+        const float4* wo4 = reinterpret_cast<const float4*>(s_wout);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float4 g = grow[c * 4 + e];
+            const float4 wv = wo4[c * 4 + e];
+            logit = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 0]) + g.x, 0.0f), wv.x, logit);
+            logit = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 1]) + g.y, 0.0f), wv.y, logit);
+            logit = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 2]) + g.z, 0.0f), wv.z, logit);
+            logit = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 3]) + g.w, 0.0f), wv.w, logit);
+          }
+        }
+      }
+      tc::tc_fence_before_sync();          // my TMEM reads are ordered before the next tile's barrier / MMA
+      const float sigma = softplus(logit);
+      __syncwarp();                        // w_taps / w_gi are rewritten by the next sub-tile
+
+      // ---------------- C, D ----------------
+      const float wgt = composite_chunk(p, lane, k, K, active, z, z_next, sigma, sample_id, T_carry, depth_part, wsum_part);
+      colour_views<false>(p, lane, b, X, Y, Z, active, inv_f, wgt, sample_id, w_rgb);
+      __syncwarp();
+    }
+    if (active) finish_ray(p, lane, ray, depth_part, wsum_part, w_rgb);
+    __syncwarp();
+  }
+
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<kTmemCols>(tmem);
+}
+
+}  // namespace tcr
+
+bool tc_supported(const KernelParams& p) {
+  const BtsRenderCfg& c = p.cfg;
+  return p.mlp.Hd == 64 && p.mlp.n_blocks == 0 && p.mlp.P == 39 && c.num_freqs == 6 && c.include_input &&
+         c.n_coarse % 32 == 0 && p.scene.Vc <= kMaxColorViews;
+}
+
+cudaError_t launch_tc(const KernelParams& p, cudaStream_t stream) {
+  auto kern = p.cfg.precision == 0 ? tcr::render_tc_kernel<true> : tcr::render_tc_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tcr::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 148, occ = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, tcr::kThreads, tcr::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) return cudaErrorInvalidConfiguration;
+  if (occ > 4) occ = 4;                                   // 512 TMEM columns / 128 per CTA
+  const int64_t n_pass = (p.n_items + 3) / 4;
+  const int64_t cap = (int64_t)sms * occ;                 // persistent: every CTA resident, strided over passes
+  const int grid = (int)(n_pass < cap ? n_pass : cap);
+  kern<<<grid, tcr::kThreads, tcr::kSmemBytes, stream>>>(p);
+  return cudaGetLastError();
+}
+
+int tc_barrier_timeouts() {
+  int v = 0;
+  cudaMemcpyFromSymbol(&v, g_tc_barrier_timeouts, sizeof(int));
+  return v;
+}
+
+}  // namespace bts

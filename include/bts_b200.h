@@ -91,7 +91,9 @@ typedef struct {
   float z_range;           /* float(d_max - d_min)                   models_bts.py:162   */
   const float* z_steps;    /* (K) device: torch.linspace(0, 1 - 1/K, K)   nerf.py:114    */
   float step;              /* float(1.0 / K)                              nerf.py:112    */
-  int32_t precision;       /* 0 = exact fp32 tier, 1 = fast (single-pass tensor-core) tier */
+  int32_t precision;       /* 0 = exact tier (tensor-core kernel with two-term operand split where the config
+                              allows it, else the general fp32 kernel), 1 = fast tier (single-pass tensor core),
+                              2 = exact tier forced onto the general CUDA-core kernel */
 } BtsRenderCfg;
 
 /* Optional outputs of NeRFRenderer._format_outputs (nerf.py:377-401).  NULL = not wanted (not computed/written). */
@@ -137,6 +139,10 @@ int bts_query_field(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg
 
 /* Name of the kernel family the last bts_render_fwd on this thread dispatched to ("general" | "tc"), for tests. */
 const char* bts_last_kernel(void);
+
+/* Debug/test hook (synchronises): number of bounded mbarrier waits that expired inside the tensor-core kernel since
+ * the library was loaded.  Always 0 unless the kernel has a pipeline bug. */
+int bts_debug_tc_timeouts(void);
 
 #ifdef __cplusplus
 }

@@ -19,8 +19,9 @@ def workload_from_golden(g):
                         rays=g.rays, u=g.u.reshape(-1, K))
 
 
-def cuda_render(wl, state_dict=None, device="cuda", use_u=True, **wants):
+def cuda_render(wl, state_dict=None, device="cuda", use_u=True, precision=0, **wants):
     net, wrapped = syn.build_model(wl, device, state_dict=state_dict)
+    wrapped.renderer.precision = precision
     with torch.no_grad():
         net.encode(wl.images.to(device), wl.Ks.to(device), wl.poses_c2w.to(device), ids_encoder=wl.ids_encoder,
                    ids_render=wl.ids_render)

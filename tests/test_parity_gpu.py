@@ -43,6 +43,41 @@ def test_point_query_matches_reference_fixture(name):
     assert torch.equal(d_sig, sig)
 
 
+def _last_kernel():
+    return _lib.load().bts_last_kernel().decode()
+
+
+def test_tensor_core_kernel_is_dispatched_and_matches_general_kernel():
+    """cfg2 takes the tcgen05 kernel (exact tier); it must agree with the fp32 CUDA-core kernel and the oracle, and no
+    bounded barrier wait may expire."""
+    wl = syn.cfg2_kitti360_eval(H=96, W=320, stereo=True, lin_out_bias=-4.0, seed=31, ray_subsample=20001)
+    sd_net, _ = syn.build_model(wl, "cpu")
+    sd = {k: v.clone() for k, v in sd_net.state_dict().items() if not k.startswith("encoder.")}
+    _, _, tc = pu.cuda_render(wl, state_dict=sd, precision=0, **ALL)
+    assert _last_kernel() == "tc"
+    _, _, gen = pu.cuda_render(wl, state_dict=sd, precision=2, **ALL)
+    assert _last_kernel() == "general"
+    assert _lib.load().bts_debug_tc_timeouts() == 0
+    ref = pu.oracle_render(wl, sd, **ALL)
+    print("tc vs oracle", pu.compare_render(wl, tc, ref, label="tc"))
+    print("general vs oracle", pu.compare_render(wl, gen, ref, label="general"))
+    print("tc vs general", pu.compare_render(wl, tc, gen, label="tc-vs-general"))
+
+
+def test_fast_tier_within_its_stated_tolerance():
+    """precision=1 (single-pass fp16/tf32 operands): depth abs_rel <= 1e-3 (SURVEY.md §8d fast tier), in practice ~1e-5."""
+    wl = syn.cfg2_kitti360_eval(H=96, W=320, stereo=True, lin_out_bias=-4.0, seed=32, ray_subsample=20000)
+    sd_net, _ = syn.build_model(wl, "cpu")
+    sd = {k: v.clone() for k, v in sd_net.state_dict().items() if not k.startswith("encoder.")}
+    _, _, fast = pu.cuda_render(wl, state_dict=sd, precision=1, want_weights=True)
+    assert _last_kernel() == "tc"
+    ref = pu.oracle_render(wl, sd, want_weights=True)
+    same = (fast["invalid"] == ref["invalid"]).flatten(2).all(-1)
+    rel = ((fast["depth"] - ref["depth"]).abs() / ref["depth"])[same]
+    print("fast tier: abs_rel", rel.mean().item(), "max", rel.max().item(), "weights", (fast["weights"] - ref["weights"])[same].abs().max().item())
+    assert rel.mean().item() <= 1e-3 and (fast["weights"] - ref["weights"])[same].abs().max().item() <= 5e-3
+
+
 def _full_size_case(wl, wants, lin_out_bias):
     sd_net, _ = syn.build_model(wl, "cpu")
     sd = {k: v.clone() for k, v in sd_net.state_dict().items() if not k.startswith("encoder.")}
