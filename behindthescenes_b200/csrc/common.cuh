@@ -51,7 +51,8 @@ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t ray, uin
     k0 += 0x9E3779B9u;
     k1 += 0xBB67AE85u;
   }
-  const uint32_t x = c[k & 3];
+  const uint32_t sel = k & 3;                       // select without indexing (keeps c[] in registers)
+  const uint32_t x = sel == 0 ? c[0] : (sel == 1 ? c[1] : (sel == 2 ? c[2] : c[3]));
   return (float)(x >> 8) * (1.0f / 16777216.0f);
 }
 

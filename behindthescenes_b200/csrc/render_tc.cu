@@ -47,6 +47,7 @@ constexpr int kWarpGi = 32 * 8 * 4;                  // [32][68] floats
 constexpr int kWarpRgb = kWarpGi + 32 * kGiStride * 4;
 constexpr int kWarpBytes = kWarpRgb + kMaxColorViews * 4 * 4;
 constexpr int kSmemBytes = kOffWarp + 4 * kWarpBytes;
+static_assert(4 * (kSmemBytes + 1024) <= 233472, "4 CTAs per SM must fit the 228 KB shared memory of an SM");
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
@@ -169,12 +170,12 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
         w_taps[lane * 2 + 0] = a;
         w_taps[lane * 2 + 1] = w;
       }
+      const bool big = fmaxf(fabsf(pv[0]), fmaxf(fabsf(pv[1]), fabsf(pv[2]))) > kPeFastLimit;
       {
         uint32_t ahi[24], alo[24], araw[8];
 #pragma unroll
         for (int i = 18; i < 24; ++i) { ahi[i] = 0u; alo[i] = 0u; }
         const float kHalfPi = 1.57079637050628662109375f;
-        const bool big = fmaxf(fabsf(pv[0]), fmaxf(fabsf(pv[1]), fabsf(pv[2]))) > kPeFastLimit;
         if (!big) {
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
@@ -202,11 +203,13 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
             }
           }
         }
+        // raw coordinates: tf32 hi/lo through the tensor core when they are O(1); far-outside samples (|p| in the
+        // thousands, clamped z) would lose absolute accuracy in a two-term split, they are added in fp32 in P3 instead
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
           const float h = tf32_hi(pv[d]);
-          araw[d] = __float_as_uint(h);
-          araw[3 + d] = kExact ? __float_as_uint(pv[d] - h) : 0u;
+          araw[d] = big ? 0u : __float_as_uint(h);
+          araw[3 + d] = (kExact && !big) ? __float_as_uint(pv[d] - h) : 0u;
         }
         araw[6] = 0u; araw[7] = 0u;
 #pragma unroll
@@ -291,16 +294,37 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
         tc::tmem_ld_wait();
         const float4* grow = reinterpret_cast<const float4*>(w_gi + lane * kGiStride);
         const float4* wo4 = reinterpret_cast<const float4*>(s_wout);
+        if (!big) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 4; ++c) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float4 g = grow[c * 4 + e];
-            const float4 wv = wo4[c * 4 + e];
-            logit = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 0]) + g.x, 0.0f), wv.x, logit);
-            logit = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 1]) + g.y, 0.0f), wv.y, logit);
-            logit = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 2]) + g.z, 0.0f), wv.z, logit);
-            logit = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 3]) + g.w, 0.0f), wv.w, logit);
+            for (int e = 0; e < 4; ++e) {
+              const float4 g = grow[c * 4 + e];
+              const float4 wv = wo4[c * 4 + e];
+              logit = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 0]) + g.x, 0.0f), wv.x, logit);
+              logit = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 1]) + g.y, 0.0f), wv.y, logit);
+              logit = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 2]) + g.z, 0.0f), wv.z, logit);
+              logit = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 3]) + g.w, 0.0f), wv.w, logit);
+            }
+          }
+        } else {   // rare: raw-coordinate part of lin_in in fp32
+          const float4* wrh = reinterpret_cast<const float4*>(smem + kOffWrawA);   // chunk 0: [hi0 hi1 hi2 hi0]
+          const float4* wrl = reinterpret_cast<const float4*>(smem + kOffWrawB);   // chunk 0: [lo0 lo1 lo2 0]; hi+lo = fp32 weight
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float4 g = grow[c * 4 + e];
+              const float4 wv = wo4[c * 4 + e];
+              const float gv[4] = {g.x, g.y, g.z, g.w}, wo[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float4 wh = wrh[c * 16 + e * 4 + t], wl = wrl[c * 16 + e * 4 + t];
+                float h = __uint_as_float(dv[c][e * 4 + t]) + gv[t];
+                h = fmaf(wh.z + wl.z, pv[2], fmaf(wh.y + wl.y, pv[1], fmaf(wh.x + wl.x, pv[0], h)));
+                logit = fmaf(fmaxf(h, 0.0f), wo[t], logit);
+              }
+            }
           }
         }
       }
@@ -334,13 +358,14 @@ cudaError_t launch_tc(const KernelParams& p, cudaStream_t stream) {
   auto kern = p.cfg.precision == 0 ? tcr::render_tc_kernel<true> : tcr::render_tc_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tcr::kSmemBytes);
   if (e != cudaSuccess) return e;
-  int dev = 0, sms = 148, occ = 1;
+  // 4 CTAs/SM by design (128 regs x 128 threads, 56 KB smem, 128 of 512 TMEM columns each): ask for the full
+  // shared-memory carve-out, otherwise the default split leaves room for a single CTA.
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, tcr::kThreads, tcr::kSmemBytes);
-  if (e != cudaSuccess) return e;
-  if (occ < 1) return cudaErrorInvalidConfiguration;
-  if (occ > 4) occ = 4;                                   // 512 TMEM columns / 128 per CTA
+  const int occ = 4;
   const int64_t n_pass = (p.n_items + 3) / 4;
   const int64_t cap = (int64_t)sms * occ;                 // persistent: every CTA resident, strided over passes
   const int grid = (int)(n_pass < cap ? n_pass : cap);

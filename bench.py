@@ -99,6 +99,32 @@ def cpu_reference_run(wl, sd, n_rays, steps, warmup):
     return sum(times) / len(times), out
 
 
+def gpu_eager_reference_run(wl, sd, dev, steps=3, warmup=1):
+    """The reference's own render path as it would run on this GPU: the oracle's torch op chain (same ops, same
+    100000-point chunking as nerf.py:244-268) on CUDA tensors, fp32 (TF32 matmul off = torch default).  Baseline only."""
+    from oracle import bts_oracle as orc
+    from tests.golden_io import mlp_params
+    mv = lambda t: t.to(dev)  # noqa: E731
+    st = orc.encode_state(mv(wl.images), mv(wl.Ks), mv(wl.poses_c2w), mv(wl.feats), wl.ids_encoder, wl.ids_render)
+    fcfg = orc.FieldConfig.from_model_conf(wl.model_conf)
+    rcfg = orc.RenderConfig.from_renderer_conf(wl.renderer_conf)
+    mlp = {k: mv(v) for k, v in mlp_params(sd).items()}
+    ef = mv(sd["empty_feature"]) if "empty_feature" in sd else None
+    rays, u = mv(wl.rays), mv(wl.u)
+    evs = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = orc.render(st, mlp, fcfg, rcfg, rays, u=u, empty_feature=ef, want_weights=True, want_alphas=True)["coarse"]
+            b.record()
+            if i >= warmup:
+                evs.append((a, b))
+        torch.cuda.synchronize(dev)
+    ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+    return ms, out
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -322,6 +348,14 @@ def run_ours(args):
             line["depth_abs_rel_vs_ref"] = {"all_rays": rel.mean().item(), "rays_without_knife_edge_flag_flip": rel[same].mean().item(),
                                             "max_abs_weights": (ours["weights"].cpu() - ref_out["weights"])[same].abs().max().item(),
                                             "rays": n_s, "flag_flip_rays": int((~same).sum().item())}
+        if world == 1 and not args.no_ref_gpu:
+            try:
+                ms, ref_gpu = gpu_eager_reference_run(wl, sd, dev)
+                line["ref_eager_gpu"] = {"value": n_frame / (ms * 1e-3), "unit": "rays/s", "ms_per_frame": ms,
+                                         "what": "reference op chain (oracle port) in eager PyTorch on this GPU, fp32, 100000-point chunks, same frame and outputs",
+                                         "speedup_ours_vs_it": value / (n_frame / (ms * 1e-3))}
+            except Exception as e:  # baseline only: never fail the bench because of it
+                line["ref_eager_gpu"] = {"unavailable": repr(e)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -336,6 +370,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", type=int, default=0, help="0 exact-fp32 tier, 1 fast tier")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the eager-PyTorch-on-GPU reference leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

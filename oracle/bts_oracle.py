@@ -122,10 +122,10 @@ def positional_encoding(x: torch.Tensor, num_freqs: int, freq_factor: float, inc
     """models/common/model/code.py:12-42: out = [x, sin(f0 x), sin(f0 x + pi/2), sin(f1 x), ...] with
     f_i = freq_factor * 2^i; layout octave-major, then (sin, cos), then input dim."""
     freqs = freq_factor * 2.0 ** torch.arange(0, num_freqs)
-    fr = torch.repeat_interleave(freqs, 2).view(1, -1, 1)            # :21-23
+    fr = torch.repeat_interleave(freqs, 2).view(1, -1, 1).to(x.device)   # :21-23 (registered buffers follow the module)
     ph = torch.zeros(2 * num_freqs)
     ph[1::2] = math.pi * 0.5                                         # :26-28
-    ph = ph.view(1, -1, 1)
+    ph = ph.view(1, -1, 1).to(x.device)
     rep = x.unsqueeze(1).repeat(1, num_freqs * 2, 1)                 # :37
     emb = torch.sin(torch.addcmul(ph, rep, fr)).view(x.shape[0], -1)  # :38-39
     return torch.cat((x, emb), dim=-1) if include_input else emb      # :40-41
@@ -189,7 +189,7 @@ def field_forward(st: FieldState, mlp: Dict[str, torch.Tensor], cfg: FieldConfig
     sigma = F.softplus(mlp_resnetfc(x, mlp, cfg.n_blocks)[..., :1])   # :294-313
     Vc = st.imgs.shape[1]
     if only_density:                                                  # :335-337 -- invalid keeps the view axis:
-        return torch.zeros((n, P, Vc * 3)), inv_f_views.to(sigma.dtype), sigma   # (n,Vf,P,1), see :283 + :337
+        return torch.zeros((n, P, Vc * 3), device=sigma.device), inv_f_views.to(sigma.dtype), sigma   # (n,Vf,P,1), see :283 + :337
     uvc, _, _, inv_c = _project(xyz, st.Kc, st.Mc)                    # :221-232
     col = _bilinear_border(st.imgs, uvc)                              # (n,Vc,P,Cc)  :234
     Cc = col.shape[-1]
@@ -207,7 +207,7 @@ def stratified_depths(rays: torch.Tensor, n_coarse: int, lindisp: bool, u: Optio
     """nerf.py:103-123.  rays (B,8); u (B,K) jitter in [0,1) (``torch.rand_like`` in the reference)."""
     near, far = rays[:, -2:-1], rays[:, -1:]
     step = 1.0 / n_coarse
-    steps = torch.linspace(0, 1 - step, n_coarse).unsqueeze(0).repeat(rays.shape[0], 1)
+    steps = torch.linspace(0, 1 - step, n_coarse, device=rays.device).unsqueeze(0).repeat(rays.shape[0], 1)
     if u is None:
         u = torch.rand_like(steps)
     steps = steps + u * step

@@ -15,9 +15,9 @@ if [ -n "$RUN_REF" ]; then echo "== bench reference arm" ; timeout 600 python be
 if [ -z "$SKIP_NCU" ]; then
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_launch_bench.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-ref-gpu > $OUT/ncu_launch_bench.log 2>&1
 echo "== ncu full capture (render kernel)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:render_ -s 3 -c 1 -f -o $OUT/render_full \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_bench.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-ref-gpu > $OUT/ncu_full_bench.log 2>&1
 fi
 ls -la $OUT
