@@ -32,28 +32,18 @@ struct KernelParams {
 
 // ------------------------------------------------------------------------------------------------------------------
 // Counter-based generator for the stratified jitter when the caller does not inject `u`
-// (the reference draws torch.rand_like, models/common/render/nerf.py:116).  Philox4x32-10, key = seed,
-// counter = (ray, sample/4); uniform = top 24 bits * 2^-24 in [0,1) like torch's float uniform.
+// (the reference draws torch.rand_like, models/common/render/nerf.py:116).  Stateless: two rounds of the murmur3
+// 32-bit finaliser over (seed, ray, sample) -- every (ray, sample) gets an independent-looking uniform, reproducible
+// per seed, ~14 instructions.  uniform = top 24 bits * 2^-24 in [0,1) like torch's float uniform.
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-  const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
-  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
 }
-
-__device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t ray, uint32_t k) {
-  uint32_t c[4] = {(uint32_t)ray, (uint32_t)(ray >> 32), k >> 2, 0x42545342u};
-  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    philox_round(c, k0, k1);
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-  const uint32_t sel = k & 3;                       // select without indexing (keeps c[] in registers)
-  const uint32_t x = sel == 0 ? c[0] : (sel == 1 ? c[1] : (sel == 2 ? c[2] : c[3]));
-  return (float)(x >> 8) * (1.0f / 16777216.0f);
+__device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t ray, uint32_t k) {
+  uint32_t h = fmix32((uint32_t)ray ^ (uint32_t)seed);
+  h = fmix32(h ^ ((uint32_t)(ray >> 32) * 0x9E3779B1u) ^ (k * 0x85EBCA77u + 0x165667B1u) ^ (uint32_t)(seed >> 32));
+  return (float)(h >> 8) * (1.0f / 16777216.0f);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -61,7 +51,7 @@ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t ray, uin
 // elementwise ops (no FMA contraction): steps = linspace[k] + u*step;  lindisp: 1/(1/near*(1-s) + 1/far*s).
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float sample_depth(const KernelParams& p, int64_t ray, int k, float near_, float far_) {
-  const float uu = p.u ? __ldg(p.u + ray * p.cfg.n_coarse + k) : philox_uniform(p.seed, (uint64_t)ray, (uint32_t)k);
+  const float uu = p.u ? __ldg(p.u + ray * p.cfg.n_coarse + k) : hash_uniform(p.seed, (uint64_t)ray, (uint32_t)k);
   const float s = __fadd_rn(__ldg(p.cfg.z_steps + k), __fmul_rn(uu, p.cfg.step));
   const float one_m = __fsub_rn(1.0f, s);
   if (p.cfg.lindisp) {

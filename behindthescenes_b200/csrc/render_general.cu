@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) render_general_kernel(const
     float ro[3] = {0, 0, 0}, rd[3] = {0, 0, 0}, near_ = 0, far_ = 0;
     int64_t b;
     if (!kPoints) {
-      b = item / p.per_batch;
+      b = p.scene.n == 1 ? 0 : item / p.per_batch;
       const float rv = lane < 8 ? __ldg(p.rays + item * 8 + lane) : 0.0f;
       ro[0] = __shfl_sync(0xffffffffu, rv, 0); ro[1] = __shfl_sync(0xffffffffu, rv, 1);
       ro[2] = __shfl_sync(0xffffffffu, rv, 2); rd[0] = __shfl_sync(0xffffffffu, rv, 3);
@@ -107,6 +107,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) render_general_kernel(const
     if (lane < kMaxColorViews * 4) w_rgb[lane] = 0.0f;
     __syncwarp();
 
+    float z_ahead = 0.0f;   // depths are produced one chunk ahead (delta needs z[k+1])
+    if (!kPoints && lane < K) z_ahead = sample_depth(p, item, lane, near_, far_);
     for (int c0 = 0; c0 < K; c0 += 32) {
       const int k = c0 + lane;
       int64_t sample_id;  // flat index of this lane's sample/point
@@ -116,9 +118,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) render_general_kernel(const
       if (!kPoints) {
         valid = k < K;
         sample_id = item * K + k;
-        if (valid) z = sample_depth(p, item, k, near_, far_);
+        z = z_ahead;
+        z_ahead = (k + 32 < K) ? sample_depth(p, item, k + 32, near_, far_) : 0.0f;
         z_next = __shfl_down_sync(0xffffffffu, z, 1);
-        if (lane == 31 && k + 1 < K) z_next = sample_depth(p, item, k + 1, near_, far_);
+        const float z_first_of_next = __shfl_sync(0xffffffffu, z_ahead, 0);
+        if (lane == 31) z_next = z_first_of_next;
         X = __fadd_rn(ro[0], __fmul_rn(z, rd[0]));   // nerf.py:231 (separate mul and add)
         Y = __fadd_rn(ro[1], __fmul_rn(z, rd[1]));
         Z = __fadd_rn(ro[2], __fmul_rn(z, rd[2]));

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
     const int64_t ray_raw = pass * 4 + warp;
     const bool active = ray_raw < n_rays;
     const int64_t ray = active ? ray_raw : n_rays - 1;
-    const int64_t b = ray / p.per_batch;
+    const int64_t b = p.scene.n == 1 ? 0 : ray / p.per_batch;   // 64-bit division only for batched scenes
     const float rv = lane < 8 ? __ldg(p.rays + ray * 8 + lane) : 0.0f;
     const float ro0 = __shfl_sync(0xffffffffu, rv, 0), ro1 = __shfl_sync(0xffffffffu, rv, 1), ro2 = __shfl_sync(0xffffffffu, rv, 2);
     const float rd0 = __shfl_sync(0xffffffffu, rv, 3), rd1 = __shfl_sync(0xffffffffu, rv, 4), rd2 = __shfl_sync(0xffffffffu, rv, 5);
@@ -145,19 +145,23 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
     View vf;
     load_view(vf, p.scene.K_f + b * 9, p.scene.w2c_f + b * 16);
 
+    float z_ahead = sample_depth(p, ray, lane, near_, far_);   // depths are produced one chunk ahead (delta needs z[k+1])
     for (int c0 = 0; c0 < K; c0 += 32) {
       const int k = c0 + lane;
       const int64_t sample_id = ray * K + k;
       // ---------------- P1: per-sample scalar work, A operand -> TMEM ----------------
-      const float z = sample_depth(p, ray, k, near_, far_);
+      const float z = z_ahead;
+      z_ahead = (c0 + 32 < K) ? sample_depth(p, ray, k + 32, near_, far_) : 0.0f;
       float z_next = __shfl_down_sync(0xffffffffu, z, 1);
-      if (lane == 31 && k + 1 < K) z_next = sample_depth(p, ray, k + 1, near_, far_);
+      const float z_first_of_next = __shfl_sync(0xffffffffu, z_ahead, 0);
+      if (lane == 31) z_next = z_first_of_next;
       const float X = __fadd_rn(ro0, __fmul_rn(z, rd0));   // nerf.py:231
       const float Y = __fadd_rn(ro1, __fmul_rn(z, rd1));
       const float Z = __fadd_rn(ro2, __fmul_rn(z, rd2));
       const Proj pf = project(vf, X, Y, Z);
       const bool inv_f = pf.invalid;
       const float pv[3] = {pf.u, pf.v, depth_code(cfg, pf)};
+      bool any_empty;
       {
         const Taps t = bilinear_taps(pf.u, pf.v, H, W);
         const int p00 = (int)((b * H + t.y0) * (int64_t)W + t.x0);
@@ -166,6 +170,7 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
         a.y = __int_as_float(t.dx * 16);
         a.z = __int_as_float(t.dy * W * 16);
         a.w = __int_as_float((use_empty && inv_f) ? 1 : 0);
+        any_empty = __any_sync(0xffffffffu, use_empty && inv_f);
         w.x = t.wx0 * t.wy0; w.y = t.wx1 * t.wy0; w.z = t.wx0 * t.wy1; w.w = t.wx1 * t.wy1;
         w_taps[lane * 2 + 0] = a;
         w_taps[lane * 2 + 1] = w;
@@ -254,26 +259,45 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
       // ---------------- P2: coalesced bilinear gather of G, half-warp per sample ----------------
       {
         const int hw = lane >> 4, q = lane & 15;
-        const float4* G4 = reinterpret_cast<const float4*>(p.scene.G);
+        const float4* G4 = reinterpret_cast<const float4*>(p.scene.G) + q;
+        if (!any_empty) {
 #pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-          const int s = 2 * i + hw;
-          const float4 a = w_taps[s * 2 + 0];
-          const float4 w = w_taps[s * 2 + 1];
-          float4 g;
-          if (__float_as_int(a.w)) {
-            g = reinterpret_cast<const float4*>(s_gempty)[q];
-          } else {
-            const float4* g00 = G4 + (size_t)(uint32_t)__float_as_int(a.x) + q;
+          for (int i = 0; i < 16; ++i) {
+            const int s = 2 * i + hw;
+            const float4 a = w_taps[s * 2 + 0];
+            const float4 w = w_taps[s * 2 + 1];
+            const float4* g00 = G4 + (uint32_t)__float_as_int(a.x);
             const float4* g10 = g00 + __float_as_int(a.z);
             const float4 v00 = __ldg(g00), v01 = __ldg(g00 + __float_as_int(a.y));
             const float4 v10 = __ldg(g10), v11 = __ldg(g10 + __float_as_int(a.y));
+            float4 g;
             g.x = fmaf(v11.x, w.w, fmaf(v10.x, w.z, fmaf(v01.x, w.y, v00.x * w.x)));
             g.y = fmaf(v11.y, w.w, fmaf(v10.y, w.z, fmaf(v01.y, w.y, v00.y * w.x)));
             g.z = fmaf(v11.z, w.w, fmaf(v10.z, w.z, fmaf(v01.z, w.y, v00.z * w.x)));
             g.w = fmaf(v11.w, w.w, fmaf(v10.w, w.z, fmaf(v01.w, w.y, v00.w * w.x)));
+            *reinterpret_cast<float4*>(w_gi + s * kGiStride + q * 4) = g;
           }
-          *reinterpret_cast<float4*>(w_gi + s * kGiStride + q * 4) = g;
+        } else {   // some samples of this chunk left the encoder frustum: they take the learned empty row
+#pragma unroll 2
+          for (int i = 0; i < 16; ++i) {
+            const int s = 2 * i + hw;
+            const float4 a = w_taps[s * 2 + 0];
+            const float4 w = w_taps[s * 2 + 1];
+            float4 g;
+            if (__float_as_int(a.w)) {
+              g = reinterpret_cast<const float4*>(s_gempty)[q];
+            } else {
+              const float4* g00 = G4 + (uint32_t)__float_as_int(a.x);
+              const float4* g10 = g00 + __float_as_int(a.z);
+              const float4 v00 = __ldg(g00), v01 = __ldg(g00 + __float_as_int(a.y));
+              const float4 v10 = __ldg(g10), v11 = __ldg(g10 + __float_as_int(a.y));
+              g.x = fmaf(v11.x, w.w, fmaf(v10.x, w.z, fmaf(v01.x, w.y, v00.x * w.x)));
+              g.y = fmaf(v11.y, w.w, fmaf(v10.y, w.z, fmaf(v01.y, w.y, v00.y * w.x)));
+              g.z = fmaf(v11.z, w.w, fmaf(v10.z, w.z, fmaf(v01.z, w.y, v00.z * w.x)));
+              g.w = fmaf(v11.w, w.w, fmaf(v10.w, w.z, fmaf(v01.w, w.y, v00.w * w.x)));
+            }
+            *reinterpret_cast<float4*>(w_gi + s * kGiStride + q * 4) = g;
+          }
         }
       }
       __syncwarp();

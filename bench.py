@@ -313,7 +313,7 @@ def run_ours(args):
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(tp):
-            traffic = json.load(open(tp)).get(kernel_name)
+            traffic = (json.load(open(tp)).get(kernel_name) or {}).get("dram_bytes_per_launch")
         if f_t >= f_h:
             roof = {"bound": "tensor", "achieved": tf_ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": f_t}
         else:
