@@ -10,7 +10,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libbts_b200.so")
 
 BTS_MAX_BLOCKS = 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 _fp = C.POINTER(C.c_float)
 
 
@@ -43,6 +43,15 @@ class BtsRenderOut(C.Structure):
                 ("alphas", C.c_void_p), ("z_samps", C.c_void_p), ("rgb_samps", C.c_void_p)]
 
 
+class BtsRenderGrad(C.Structure):
+    _fields_ = [("rgb", C.c_void_p), ("depth", C.c_void_p), ("weights", C.c_void_p), ("alphas", C.c_void_p)]
+
+
+class BtsParamGrad(C.Structure):
+    _fields_ = [("d_G", C.c_void_p), ("d_g_empty", C.c_void_p), ("d_w_pe", C.c_void_p), ("d_w_out", C.c_void_p),
+                ("d_b_out", C.c_void_p)]
+
+
 EXPORTS = {
     "bts_abi_version": (C.c_int, []),
     "bts_last_error": (C.c_char_p, []),
@@ -53,6 +62,9 @@ EXPORTS = {
     "bts_pack_images": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "bts_render_fwd": (C.c_int, [C.POINTER(BtsScene), C.POINTER(BtsMlp), C.POINTER(BtsRenderCfg), C.c_void_p,
                                  C.c_int64, C.c_int64, C.c_void_p, C.c_uint64, C.POINTER(BtsRenderOut), C.c_void_p]),
+    "bts_render_bwd": (C.c_int, [C.POINTER(BtsScene), C.POINTER(BtsMlp), C.POINTER(BtsRenderCfg), C.c_void_p,
+                                 C.c_int64, C.c_int64, C.c_void_p, C.c_uint64, C.POINTER(BtsRenderGrad),
+                                 C.POINTER(BtsParamGrad), C.c_void_p]),
     "bts_query_field": (C.c_int, [C.POINTER(BtsScene), C.POINTER(BtsMlp), C.POINTER(BtsRenderCfg), C.c_void_p,
                                   C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

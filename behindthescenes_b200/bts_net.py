@@ -243,7 +243,30 @@ class BTSNet(nn.Module):
     def render_rays(self, renderer, rays, u=None, seed=0, want_weights=False, want_alphas=False, want_z_samps=False,
                     want_rgb_samps=False):
         """Fused sampling + field + compositing for ``NeRFRenderer.forward`` (coarse pass).
-        rays (n,R,8) -> dict of fresh tensors with the reference's shapes (nerf.py:377-401)."""
+        rays (n,R,8) -> dict of fresh tensors with the reference's shapes (nerf.py:377-401).  When gradients are
+        enabled and the MLP / empty feature / encoder features require them, the call is recorded for autograd and
+        ``loss.backward()`` runs ``bts_render_bwd`` (the reference differentiates its op chain with torch autograd,
+        ``utils/base_trainer.py:297``)."""
+        wants = dict(want_weights=want_weights, want_alphas=want_alphas, want_z_samps=want_z_samps,
+                     want_rgb_samps=want_rgb_samps)
+        if torch.is_grad_enabled():
+            feats = self.grid_f_features[self._scale] if self.grid_f_features is not None else None
+            m = self.mlp_coarse
+            diff = [feats, m.lin_in.weight, m.lin_in.bias, m.lin_out.weight, m.lin_out.bias,
+                    self.empty_feature if self.learn_empty else None]
+            if any(t is not None and t.requires_grad for t in diff):
+                if m.n_blocks != 0:
+                    raise NotImplementedError("backward of the B200 render path implements n_blocks = 0")
+                keys = ["rgb", "depth", "invalid"] + [k for k, w in (("weights", want_weights), ("alphas", want_alphas),
+                                                                    ("z_samps", want_z_samps), ("rgb_samps", want_rgb_samps)) if w]
+                ef = diff[5] if diff[5] is not None else torch.zeros(0, device=rays.device)
+                outs = _RenderFunction.apply(self, renderer, rays, u, seed, wants, tuple(keys), diff[0], diff[1], diff[2],
+                                             diff[3], diff[4], ef)
+                return dict(zip(keys, outs))
+        return self._render_rays_raw(renderer, rays, u, seed, **wants)
+
+    def _render_rays_raw(self, renderer, rays, u=None, seed=0, want_weights=False, want_alphas=False, want_z_samps=False,
+                         want_rgb_samps=False):
         lib = _lib.load()
         rays_d = _dev_f32(rays)
         self._require_cuda(rays_d)
@@ -276,3 +299,72 @@ class BTSNet(nn.Module):
                                 None if u_d is None else u_d.data_ptr(), int(seed) & (2 ** 64 - 1), C.byref(out), stream)
         _lib.check(rc, "bts_render_fwd")
         return ret
+
+
+class _RenderFunction(torch.autograd.Function):
+    """Autograd node of the fused render: forward = bts_fold_features + bts_render_fwd, backward = bts_render_bwd
+    (recompute per ray, scatter into dG) + the dense tail of the fold as two GEMMs."""
+
+    @staticmethod
+    def forward(ctx, net, renderer, rays, u, seed, wants, keys, feats, w_in, b_in, w_out, b_out, empty):
+        with torch.no_grad():
+            out = net._render_rays_raw(renderer, rays, u=u, seed=seed, **wants)
+        ctx.net, ctx.renderer, ctx.seed, ctx.keys = net, renderer, seed, keys
+        ctx.has_u = u is not None
+        ctx.K = int(renderer.n_coarse)
+        ctx.save_for_backward(rays, u if u is not None else rays.new_zeros(0), feats, w_in, empty)
+        res = tuple(out[k] for k in keys)
+        ctx.mark_non_differentiable(*[out[k] for k in keys if k in ("invalid", "z_samps", "rgb_samps")])
+        return res
+
+    @staticmethod
+    def backward(ctx, *grads):
+        import ctypes as C
+        net, renderer = ctx.net, ctx.renderer
+        rays, u, feats, w_in, empty = ctx.saved_tensors
+        lib = _lib.load()
+        if int(renderer.n_coarse) != ctx.K:
+            raise RuntimeError("renderer.n_coarse changed between forward and backward")
+        scene, keep = net._scene_struct()
+        mlp, keep2 = net._mlp_struct()
+        cfg, keep3 = net._cfg_struct(renderer)
+        rays_d = _dev_f32(rays)
+        n, R, _ = rays_d.shape
+        dev = rays_d.device
+        Hd, P, Cf = mlp.Hd, mlp.P, mlp.C
+        gmap = dict(zip(ctx.keys, grads))
+        up = _lib.BtsRenderGrad()
+        held = []
+        for name in ("rgb", "depth", "weights", "alphas"):
+            g = gmap.get(name)
+            if g is not None:
+                g = _dev_f32(g)
+                held.append(g)
+                setattr(up, name, g.data_ptr())
+        dG = torch.zeros((scene.n, scene.H, scene.W, Hd), device=dev, dtype=torch.float32)
+        dge = torch.zeros((Hd,), device=dev, dtype=torch.float32)
+        dwpe = torch.zeros((Hd, P), device=dev, dtype=torch.float32)
+        dwout = torch.zeros((Hd,), device=dev, dtype=torch.float32)
+        dbout = torch.zeros((1,), device=dev, dtype=torch.float32)
+        pg = _lib.BtsParamGrad()
+        pg.d_G, pg.d_g_empty, pg.d_w_pe, pg.d_w_out, pg.d_b_out = (t.data_ptr() for t in (dG, dge, dwpe, dwout, dbout))
+        u_d = _dev_f32(u.to(dev)) if ctx.has_u else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.bts_render_bwd(C.byref(scene), C.byref(mlp), C.byref(cfg), rays_d.data_ptr(), n, R,
+                                None if u_d is None else u_d.data_ptr(), int(ctx.seed) & (2 ** 64 - 1), C.byref(up),
+                                C.byref(pg), stream)
+        _lib.check(rc, "bts_render_bwd")
+        # dense tail of the fold G = F W_F^T + b_in (two plain GEMMs)
+        nb, _, _, H, W = feats.shape
+        dG2 = dG.view(nb, H * W, Hd)
+        W_F = w_in.detach()[:, :Cf]
+        f2 = feats.detach().reshape(nb, Cf, H * W)
+        d_feats = torch.einsum("npk,kc->ncp", dG2, W_F).reshape(feats.shape) if ctx.needs_input_grad[7] else None
+        d_WF = torch.einsum("npk,ncp->kc", dG2, f2)
+        d_b_in = dG2.sum((0, 1)) + dge
+        d_empty = None
+        if empty.numel() > 0:
+            d_WF = d_WF + torch.outer(dge, empty.detach())
+            d_empty = W_F.t() @ dge
+        d_w_in = torch.cat((d_WF, dwpe), dim=1)
+        return (None, None, None, None, None, None, None, d_feats, d_w_in, d_b_in, dwout.view(1, Hd), dbout, d_empty)

@@ -4,12 +4,15 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "bwd_params.cuh"
 
 namespace bts {
 cudaError_t launch_general(const KernelParams& p, bool points, cudaStream_t stream);
 size_t general_smem_bytes(int Hd, int p_pad, int n_blocks);
 cudaError_t launch_fold(const float* feat, int n, int C, int H, int W, const float* w_in, int ld, const float* b_in, int Hd,
                         const float* empty, float* G, float* g_empty, cudaStream_t stream);
+cudaError_t launch_bwd(const BwdParams& bp, cudaStream_t stream);
+size_t bwd_smem_bytes(int Hd, int p_pad, int K);
 bool tc_supported(const KernelParams& p);
 cudaError_t launch_tc(const KernelParams& p, cudaStream_t stream);
 int tc_barrier_timeouts();
@@ -104,6 +107,34 @@ int bts_render_fwd(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg*
     e = bts::launch_general(p, false, reinterpret_cast<cudaStream_t>(stream));
   }
   if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_render_fwd: %s", cudaGetErrorString(e));
+  return BTS_OK;
+}
+
+int bts_render_bwd(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg* cfg, const float* rays, int64_t n,
+                   int64_t R, const float* u_or_null, uint64_t seed, const BtsRenderGrad* upstream,
+                   const BtsParamGrad* grads, bts_stream_t stream) {
+  int rc = check_common(scene, mlp, cfg);
+  if (rc != BTS_OK) return rc;
+  if (!rays || !upstream || !grads) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_render_bwd: rays/upstream/grads is null");
+  if (n != scene->n) return fail(BTS_ERR_INVALID_ARGUMENT, "rays batch %lld != scene.n %d", (long long)n, scene->n);
+  if (cfg->n_coarse < 1 || !cfg->z_steps) return fail(BTS_ERR_INVALID_ARGUMENT, "n_coarse < 1 or z_steps null");
+  if (mlp->n_blocks != 0) return fail(BTS_ERR_UNSUPPORTED, "backward implements n_blocks = 0 (got %d)", mlp->n_blocks);
+  if (mlp->Hd > 64) return fail(BTS_ERR_UNSUPPORTED, "backward implements d_hidden <= 64 (got %d)", mlp->Hd);
+  if (mlp->P > 40) return fail(BTS_ERR_UNSUPPORTED, "backward implements a code width <= 40 (got %d)", mlp->P);
+  if (cfg->n_coarse > 256) return fail(BTS_ERR_UNSUPPORTED, "backward implements K <= 256 (got %d)", cfg->n_coarse);
+  if (upstream->rgb && scene->Vc < 1) return fail(BTS_ERR_INVALID_ARGUMENT, "rgb gradient with Vc=0");
+  if (!grads->d_G) return fail(BTS_ERR_INVALID_ARGUMENT, "grads.d_G is null");
+  if (n * R == 0) return BTS_OK;
+  bts::BwdParams bp;
+  memset(&bp, 0, sizeof(bp));
+  bp.k.scene = *scene; bp.k.mlp = *mlp; bp.k.cfg = *cfg;
+  bp.k.rays = rays; bp.k.u = u_or_null; bp.k.n_items = n * R; bp.k.per_batch = R; bp.k.seed = seed;
+  bp.k.p_pad = (mlp->P + 3) & ~3;
+  bp.g_rgb = upstream->rgb; bp.g_depth = upstream->depth; bp.g_weights = upstream->weights; bp.g_alphas = upstream->alphas;
+  bp.d_G = grads->d_G; bp.d_g_empty = grads->d_g_empty; bp.d_w_pe = grads->d_w_pe; bp.d_w_out = grads->d_w_out;
+  bp.d_b_out = grads->d_b_out;
+  const cudaError_t e = bts::launch_bwd(bp, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_render_bwd: %s", cudaGetErrorString(e));
   return BTS_OK;
 }
 

@@ -1,0 +1,20 @@
+// Parameter block of the backward kernel (shared by abi.cu and render_bwd.cu).
+#pragma once
+#include "common.cuh"
+
+namespace bts {
+struct BwdParams {
+  KernelParams k;
+  // upstream gradients (nullable), shapes as the forward outputs
+  const float* g_rgb;      // (n*R, Vc*Cc)
+  const float* g_depth;    // (n*R)
+  const float* g_weights;  // (n*R, K)
+  const float* g_alphas;   // (n*R, K)
+  // accumulated outputs (caller zero-initialises)
+  float* d_G;              // (n, H, W, Hd)
+  float* d_g_empty;        // (Hd)
+  float* d_w_pe;           // (Hd, P)
+  float* d_w_out;          // (Hd)
+  float* d_b_out;          // (1)
+};
+}  // namespace bts

@@ -1,0 +1,388 @@
+// Backward of the fused render (training path, BASELINE config 3): gradients of a scalar loss w.r.t. the folded
+// feature map G, the learned empty row, the positional-code columns of lin_in, lin_out -- given the upstream
+// gradients of the per-ray / per-sample outputs (rgb, depth, weights, alphas).
+//
+// Recompute-in-backward: nothing but the inputs is read; one warp owns one ray and makes two sweeps over its chunks.
+//   sweep 1 (forward recompute) : depth samples, projection, code, G-interpolation + contraction -> sigma; alpha, T;
+//                                  colours -> Wbar_k = dL/dw_k; per-sample scalars parked in shared memory
+//   reverse recurrence          : R_j = Wbar_{j+1} a_{j+1} + t_{j+1} R_{j+1}  (division-free suffix term of the
+//                                  transmittance product), dL/dalpha_j = Wbar_j T_j + g_alpha_j - T_j R_j,
+//                                  dL/dlogit_j = dL/dalpha_j * delta_j (1 - a_j) * sigmoid(logit_j)
+//   sweep 2 (MLP backward)      : recompute h per 8-sample block (lanes = hidden units), hbar = lbar * w_out * [h > 0];
+//                                  d w_out, d b_out, d W_pe (register accumulators, flushed once per CTA),
+//                                  d G (4 taps x Hd red.add per sample), d g_empty
+// The dense part of the chain (G = W_F F + b  ->  dF, dW_F, db_in) is two plain GEMMs done by the caller.
+//
+// Reference forward being differentiated: models/common/render/nerf.py:283-304 (alpha, cumprod, weights, rgb, depth),
+// models/bts/model/models_bts.py:138-216, :311-313 (features, softplus), resnetfc.py:132-184 (n_blocks = 0).
+// The reference gets these gradients from torch autograd; tests compare against autograd through the oracle.
+#include "common.cuh"
+#include "render_phases.cuh"
+#include "bwd_params.cuh"
+
+namespace bts {
+
+constexpr int kBwdWarps = 4;
+constexpr int kBwdMaxK = 256;
+
+template <int NU>
+__global__ void __launch_bounds__(kBwdWarps * 32) render_bwd_kernel(const BwdParams bp) {
+  extern __shared__ __align__(16) float smem[];
+  const KernelParams& p = bp.k;
+  constexpr int Hd = NU * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int P = p.mlp.P, Ppad = p.p_pad;
+  const int K = p.cfg.n_coarse;
+  const int Kpad = (K + 31) & ~31;
+  float* s_wpe = smem;                       // [Ppad][Hd]
+  float* s_wout = s_wpe + Ppad * Hd;         // [Hd]
+  float* wbase = s_wout + Hd + warp * (Ppad * 32 + 32 * 8 + 32 + 5 * Kpad);
+  float* w_pe = wbase;                       // [Ppad][32]
+  float* w_taps = w_pe + Ppad * 32;          // [32][8]
+  float* w_grgb = w_taps + 32 * 8;           // [Vc*Cc <= 32]
+  float* sc_alpha = w_grgb + 32;             // [Kpad] each
+  float* sc_T = sc_alpha + Kpad;
+  float* sc_wbar = sc_T + Kpad;
+  float* sc_fac = sc_wbar + Kpad;
+  float* sc_lbar = sc_fac + Kpad;
+
+  {
+    const int ld = p.mlp.C + P;
+    for (int i = threadIdx.x; i < Ppad * Hd; i += blockDim.x) {
+      const int j = i / Hd, n = i % Hd;
+      s_wpe[i] = j < P ? __ldg(p.mlp.w_in + (size_t)n * ld + p.mlp.C + j) : 0.0f;
+    }
+    for (int i = threadIdx.x; i < Hd; i += blockDim.x) s_wout[i] = __ldg(p.mlp.w_out + i);
+  }
+  __syncthreads();
+
+  const BtsRenderCfg& cfg = p.cfg;
+  const int Vc = p.scene.Vc, Cc = p.scene.Cc;
+  const int H = p.scene.H, W = p.scene.W, Hc = p.scene.Hc, Wc = p.scene.Wc;
+  const float b_out = __ldg(p.mlp.b_out);
+  const bool use_empty = cfg.learn_empty && p.scene.g_empty != nullptr;
+
+  // persistent per-lane gradient accumulators (this lane's NU hidden units)
+  float acc_wpe[NU][40];
+  float acc_wout[NU], acc_gempty[NU], acc_bout = 0.0f;
+#pragma unroll
+  for (int n = 0; n < NU; ++n) {
+    acc_wout[n] = 0.0f; acc_gempty[n] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 40; ++j) acc_wpe[n][j] = 0.0f;
+  }
+
+  for (int64_t ray = (int64_t)blockIdx.x * kBwdWarps + warp; ray < p.n_items; ray += (int64_t)gridDim.x * kBwdWarps) {
+    const int64_t b = p.scene.n == 1 ? 0 : ray / p.per_batch;
+    const float rv = lane < 8 ? __ldg(p.rays + ray * 8 + lane) : 0.0f;
+    const float ro0 = __shfl_sync(0xffffffffu, rv, 0), ro1 = __shfl_sync(0xffffffffu, rv, 1), ro2 = __shfl_sync(0xffffffffu, rv, 2);
+    const float rd0 = __shfl_sync(0xffffffffu, rv, 3), rd1 = __shfl_sync(0xffffffffu, rv, 4), rd2 = __shfl_sync(0xffffffffu, rv, 5);
+    const float near_ = __shfl_sync(0xffffffffu, rv, 6), far_ = __shfl_sync(0xffffffffu, rv, 7);
+    View vf;
+    load_view(vf, p.scene.K_f + b * 9, p.scene.w2c_f + b * 16);
+    if (lane < Vc * Cc) w_grgb[lane] = bp.g_rgb ? __ldg(bp.g_rgb + ray * Vc * Cc + lane) : 0.0f;
+    const float g_depth = bp.g_depth ? __ldg(bp.g_depth + ray) : 0.0f;
+    __syncwarp();
+    float g_rgb_sum = 0.0f;
+    if (cfg.white_bkgd)
+      for (int i = 0; i < Vc * Cc; ++i) g_rgb_sum += w_grgb[i];
+
+    // ======================= sweep 1: forward recompute, per-sample scalars =======================
+    float T_carry = 1.0f;
+    float z_ahead = lane < K ? sample_depth(p, ray, lane, near_, far_) : 0.0f;
+    for (int c0 = 0; c0 < K; c0 += 32) {
+      const int k = c0 + lane;
+      const bool valid = k < K;
+      const float z = z_ahead;
+      z_ahead = (k + 32 < K) ? sample_depth(p, ray, k + 32, near_, far_) : 0.0f;
+      float z_next = __shfl_down_sync(0xffffffffu, z, 1);
+      const float z_first_of_next = __shfl_sync(0xffffffffu, z_ahead, 0);
+      if (lane == 31) z_next = z_first_of_next;
+      const float X = __fadd_rn(ro0, __fmul_rn(z, rd0)), Y = __fadd_rn(ro1, __fmul_rn(z, rd1)), Z = __fadd_rn(ro2, __fmul_rn(z, rd2));
+      const Proj pf = project(vf, X, Y, Z);
+      {
+        positional_code(cfg, pf.u, pf.v, depth_code(cfg, pf), w_pe + lane, 32);
+        for (int j = P; j < Ppad; ++j) w_pe[j * 32 + lane] = 0.0f;
+        const Taps t = bilinear_taps(pf.u, pf.v, H, W);
+        float4 a, w;
+        a.x = __int_as_float((int)((b * H + t.y0) * (int64_t)W + t.x0));
+        a.y = __int_as_float(t.dx);
+        a.z = __int_as_float(t.dy * W);
+        a.w = __int_as_float((valid ? 1 : 0) | ((use_empty && pf.invalid) ? 2 : 0));
+        w.x = t.wx0; w.y = t.wx1; w.z = t.wy0; w.w = t.wy1;
+        reinterpret_cast<float4*>(w_taps)[lane * 2 + 0] = a;
+        reinterpret_cast<float4*>(w_taps)[lane * 2 + 1] = w;
+      }
+      __syncwarp();
+      float logit = 0.0f;
+      const int n_valid = min(32, K - c0);
+      for (int s0 = 0; s0 < n_valid; s0 += 8) {
+        float acc[8][NU];
+#pragma unroll
+        for (int ss = 0; ss < 8; ++ss) {
+          const float4 a = reinterpret_cast<const float4*>(w_taps)[(s0 + ss) * 2 + 0];
+          const float4 w = reinterpret_cast<const float4*>(w_taps)[(s0 + ss) * 2 + 1];
+          const int flags = __float_as_int(a.w);
+#pragma unroll
+          for (int n = 0; n < NU; ++n) {
+            float g = 0.0f;
+            if (flags & 2) g = __ldg(p.scene.g_empty + lane * NU + n);
+            else if (flags & 1) {
+              const float* g00 = p.scene.G + (size_t)__float_as_int(a.x) * Hd + lane * NU + n;
+              const float* g10 = g00 + (size_t)__float_as_int(a.z) * Hd;
+              const size_t dxo = (size_t)__float_as_int(a.y) * Hd;
+              g = fmaf(__ldg(g10 + dxo), w.y * w.w, fmaf(__ldg(g10), w.x * w.w, fmaf(__ldg(g00 + dxo), w.y * w.z, __ldg(g00) * (w.x * w.z))));
+            }
+            acc[ss][n] = g;
+          }
+        }
+        for (int j = 0; j < P; ++j) {
+          float wv[NU];
+#pragma unroll
+          for (int n = 0; n < NU; ++n) wv[n] = s_wpe[j * Hd + lane * NU + n];
+          const float4 c0v = *reinterpret_cast<const float4*>(w_pe + j * 32 + s0);
+          const float4 c1v = *reinterpret_cast<const float4*>(w_pe + j * 32 + s0 + 4);
+          const float cv[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+#pragma unroll
+          for (int ss = 0; ss < 8; ++ss)
+#pragma unroll
+            for (int n = 0; n < NU; ++n) acc[ss][n] = fmaf(wv[n], cv[ss], acc[ss][n]);
+        }
+#pragma unroll
+        for (int ss = 0; ss < 8; ++ss) {
+          float part = 0.0f;
+#pragma unroll
+          for (int n = 0; n < NU; ++n) part = fmaf(fmaxf(acc[ss][n], 0.0f), s_wout[lane * NU + n], part);
+          const float tot = warp_sum(part);
+          if (lane == s0 + ss) logit = tot + b_out;
+        }
+      }
+      const float sigma = softplus(logit);
+      __syncwarp();
+      // compositing forward (nerf.py:283-294)
+      const float delta = (k + 1 < K) ? __fsub_rn(z_next, z) : 1e10f;
+      const float e = expf(-(fabsf(delta) * fmaxf(sigma, 0.0f)));
+      float alpha = __fsub_rn(1.0f, e);
+      const bool capped = cfg.hard_alpha_cap && k == K - 1;
+      if (capped) alpha = 1.0f;
+      const float tr = valid ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;
+      float incl = tr;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl *= up;
+      }
+      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) excl = 1.0f;
+      const float Tk = T_carry * excl;
+      T_carry *= __shfl_sync(0xffffffffu, incl, 31);
+      // dL/dw_k: rgb (nerf.py:298, :301-304), depth (:299), direct weights gradient
+      float wbar = g_depth * z - g_rgb_sum;
+      if (bp.g_weights && valid) wbar += __ldg(bp.g_weights + ray * K + k);
+      if (bp.g_rgb) {
+        for (int v = 0; v < Vc; ++v) {
+          View vc;
+          load_view(vc, p.scene.K_c + (b * Vc + v) * 9, p.scene.w2c_c + (b * Vc + v) * 16);
+          const Proj pc = project(vc, X, Y, Z);
+          const Taps t = bilinear_taps(pc.u, pc.v, Hc, Wc);
+          const float4* base = reinterpret_cast<const float4*>(p.scene.img4) + ((b * Vc + v) * Hc + t.y0) * (int64_t)Wc + t.x0;
+          const float4 c00 = __ldg(base), c01 = __ldg(base + t.dx), c10 = __ldg(base + t.dy * Wc), c11 = __ldg(base + t.dy * Wc + t.dx);
+          const float w00 = t.wx0 * t.wy0, w01 = t.wx1 * t.wy0, w10 = t.wx0 * t.wy1, w11 = t.wx1 * t.wy1;
+          const float col[4] = {fmaf(c11.x, w11, fmaf(c10.x, w10, fmaf(c01.x, w01, c00.x * w00))),
+                                fmaf(c11.y, w11, fmaf(c10.y, w10, fmaf(c01.y, w01, c00.y * w00))),
+                                fmaf(c11.z, w11, fmaf(c10.z, w10, fmaf(c01.z, w01, c00.z * w00))),
+                                fmaf(c11.w, w11, fmaf(c10.w, w10, fmaf(c01.w, w01, c00.w * w00)))};
+          for (int c = 0; c < Cc; ++c) wbar = fmaf(w_grgb[v * Cc + c], col[c], wbar);
+        }
+      }
+      if (valid) {
+        sc_alpha[k] = alpha;
+        sc_T[k] = Tk;
+        sc_wbar[k] = wbar;
+        // d alpha / d logit = delta * exp(-delta sigma) * sigmoid(logit);  sigmoid(logit) = 1 - exp(-softplus(logit))
+        sc_fac[k] = capped ? 0.0f : fabsf(delta) * e * (1.0f - expf(-sigma));
+      }
+      __syncwarp();
+    }
+
+    // ======================= reverse recurrence (division-free) =======================
+    if (lane == 0) {
+      float Rj = 0.0f;   // R_{K-1} = 0
+      for (int j = K - 1; j >= 0; --j) {
+        const float a = sc_alpha[j], T = sc_T[j];
+        float abar = fmaf(sc_wbar[j], T, -T * Rj);
+        if (bp.g_alphas) abar += __ldg(bp.g_alphas + ray * K + j);
+        sc_lbar[j] = abar * sc_fac[j];
+        Rj = fmaf(sc_wbar[j], a, ((1.0f - a) + 1e-10f) * Rj);   // becomes R_{j-1}
+      }
+    }
+    __syncwarp();
+
+    // ======================= sweep 2: MLP backward =======================
+    z_ahead = lane < K ? sample_depth(p, ray, lane, near_, far_) : 0.0f;
+    for (int c0 = 0; c0 < K; c0 += 32) {
+      const int k = c0 + lane;
+      const bool valid = k < K;
+      const float z = z_ahead;
+      z_ahead = (k + 32 < K) ? sample_depth(p, ray, k + 32, near_, far_) : 0.0f;
+      const float X = __fadd_rn(ro0, __fmul_rn(z, rd0)), Y = __fadd_rn(ro1, __fmul_rn(z, rd1)), Z = __fadd_rn(ro2, __fmul_rn(z, rd2));
+      const Proj pf = project(vf, X, Y, Z);
+      {
+        positional_code(cfg, pf.u, pf.v, depth_code(cfg, pf), w_pe + lane, 32);
+        for (int j = P; j < Ppad; ++j) w_pe[j * 32 + lane] = 0.0f;
+        const Taps t = bilinear_taps(pf.u, pf.v, H, W);
+        float4 a, w;
+        a.x = __int_as_float((int)((b * H + t.y0) * (int64_t)W + t.x0));
+        a.y = __int_as_float(t.dx);
+        a.z = __int_as_float(t.dy * W);
+        a.w = __int_as_float((valid ? 1 : 0) | ((use_empty && pf.invalid) ? 2 : 0));
+        w.x = t.wx0; w.y = t.wx1; w.z = t.wy0; w.w = t.wy1;
+        reinterpret_cast<float4*>(w_taps)[lane * 2 + 0] = a;
+        reinterpret_cast<float4*>(w_taps)[lane * 2 + 1] = w;
+      }
+      __syncwarp();
+      const int n_valid = min(32, K - c0);
+      for (int s0 = 0; s0 < n_valid; s0 += 8) {
+        float acc[8][NU];
+#pragma unroll
+        for (int ss = 0; ss < 8; ++ss) {
+          const float4 a = reinterpret_cast<const float4*>(w_taps)[(s0 + ss) * 2 + 0];
+          const float4 w = reinterpret_cast<const float4*>(w_taps)[(s0 + ss) * 2 + 1];
+          const int flags = __float_as_int(a.w);
+#pragma unroll
+          for (int n = 0; n < NU; ++n) {
+            float g = 0.0f;
+            if (flags & 2) g = __ldg(p.scene.g_empty + lane * NU + n);
+            else if (flags & 1) {
+              const float* g00 = p.scene.G + (size_t)__float_as_int(a.x) * Hd + lane * NU + n;
+              const float* g10 = g00 + (size_t)__float_as_int(a.z) * Hd;
+              const size_t dxo = (size_t)__float_as_int(a.y) * Hd;
+              g = fmaf(__ldg(g10 + dxo), w.y * w.w, fmaf(__ldg(g10), w.x * w.w, fmaf(__ldg(g00 + dxo), w.y * w.z, __ldg(g00) * (w.x * w.z))));
+            }
+            acc[ss][n] = g;
+          }
+        }
+        for (int j = 0; j < P; ++j) {
+          float wv[NU];
+#pragma unroll
+          for (int n = 0; n < NU; ++n) wv[n] = s_wpe[j * Hd + lane * NU + n];
+          const float4 c0v = *reinterpret_cast<const float4*>(w_pe + j * 32 + s0);
+          const float4 c1v = *reinterpret_cast<const float4*>(w_pe + j * 32 + s0 + 4);
+          const float cv[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+#pragma unroll
+          for (int ss = 0; ss < 8; ++ss)
+#pragma unroll
+            for (int n = 0; n < NU; ++n) acc[ss][n] = fmaf(wv[n], cv[ss], acc[ss][n]);
+        }
+        // hbar[ss][n] = lbar_s * w_out[n] * [h > 0];   d w_out += lbar * relu(h);  d b_out += lbar
+        float hbar[8][NU];
+#pragma unroll
+        for (int ss = 0; ss < 8; ++ss) {
+          const int ks = c0 + s0 + ss;
+          const float lb = ks < K ? sc_lbar[ks] : 0.0f;
+          if (lane == 0) acc_bout += lb;
+#pragma unroll
+          for (int n = 0; n < NU; ++n) {
+            const float h = acc[ss][n];
+            acc_wout[n] = fmaf(lb, fmaxf(h, 0.0f), acc_wout[n]);
+            hbar[ss][n] = h > 0.0f ? lb * s_wout[lane * NU + n] : 0.0f;
+          }
+        }
+        // d W_pe[n][j] += sum_s hbar[s][n] * code[j][s]
+#pragma unroll
+        for (int j = 0; j < 40; ++j) {
+          if (j < P) {
+            const float4 c0v = *reinterpret_cast<const float4*>(w_pe + j * 32 + s0);
+            const float4 c1v = *reinterpret_cast<const float4*>(w_pe + j * 32 + s0 + 4);
+            const float cv[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+#pragma unroll
+            for (int ss = 0; ss < 8; ++ss)
+#pragma unroll
+              for (int n = 0; n < NU; ++n) acc_wpe[n][j] = fmaf(hbar[ss][n], cv[ss], acc_wpe[n][j]);
+          }
+        }
+        // d G (bilinear scatter) / d g_empty
+#pragma unroll
+        for (int ss = 0; ss < 8; ++ss) {
+          const float4 a = reinterpret_cast<const float4*>(w_taps)[(s0 + ss) * 2 + 0];
+          const float4 w = reinterpret_cast<const float4*>(w_taps)[(s0 + ss) * 2 + 1];
+          const int flags = __float_as_int(a.w);
+          if (flags & 2) {
+#pragma unroll
+            for (int n = 0; n < NU; ++n) acc_gempty[n] += hbar[ss][n];
+          } else if (flags & 1) {
+            float* g00 = bp.d_G + (size_t)__float_as_int(a.x) * Hd + lane * NU;
+            float* g10 = g00 + (size_t)__float_as_int(a.z) * Hd;
+            const size_t dxo = (size_t)__float_as_int(a.y) * Hd;
+            const float w00 = w.x * w.z, w01 = w.y * w.z, w10 = w.x * w.w, w11 = w.y * w.w;
+            if constexpr (NU == 2) {
+              const float2 hb = make_float2(hbar[ss][0], hbar[ss][1]);
+              if (hb.x != 0.0f || hb.y != 0.0f) {
+                atomicAdd(reinterpret_cast<float2*>(g00), make_float2(hb.x * w00, hb.y * w00));
+                atomicAdd(reinterpret_cast<float2*>(g00 + dxo), make_float2(hb.x * w01, hb.y * w01));
+                atomicAdd(reinterpret_cast<float2*>(g10), make_float2(hb.x * w10, hb.y * w10));
+                atomicAdd(reinterpret_cast<float2*>(g10 + dxo), make_float2(hb.x * w11, hb.y * w11));
+              }
+            } else {
+#pragma unroll
+              for (int n = 0; n < NU; ++n) {
+                const float hb = hbar[ss][n];
+                if (hb != 0.0f) {
+                  atomicAdd(g00 + n, hb * w00); atomicAdd(g00 + dxo + n, hb * w01);
+                  atomicAdd(g10 + n, hb * w10); atomicAdd(g10 + dxo + n, hb * w11);
+                }
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  // ---- flush the per-lane accumulators (one atomic per value per warp) ----
+#pragma unroll
+  for (int n = 0; n < NU; ++n) {
+    const int unit = lane * NU + n;
+    if (bp.d_w_out) atomicAdd(bp.d_w_out + unit, acc_wout[n]);
+    if (bp.d_g_empty) atomicAdd(bp.d_g_empty + unit, acc_gempty[n]);
+#pragma unroll
+    for (int j = 0; j < 40; ++j)
+      if (j < P && bp.d_w_pe) atomicAdd(bp.d_w_pe + (size_t)unit * P + j, acc_wpe[n][j]);
+  }
+  if (lane == 0 && bp.d_b_out) atomicAdd(bp.d_b_out, acc_bout);
+}
+
+size_t bwd_smem_bytes(int Hd, int p_pad, int K) {
+  const int Kpad = (K + 31) & ~31;
+  return (size_t)(p_pad * Hd + Hd + kBwdWarps * (p_pad * 32 + 32 * 8 + 32 + 5 * Kpad)) * sizeof(float);
+}
+
+template <int NU>
+static cudaError_t launch_bwd_t(const BwdParams& bp, cudaStream_t stream) {
+  const size_t smem = bwd_smem_bytes(NU * 32, bp.k.p_pad, bp.k.cfg.n_coarse);
+  auto kern = render_bwd_kernel<NU>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 148, occ = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBwdWarps * 32, smem);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) return cudaErrorInvalidConfiguration;
+  const int64_t want = (bp.k.n_items + kBwdWarps - 1) / kBwdWarps;
+  const int64_t cap = (int64_t)sms * occ;
+  const int grid = (int)(want < cap ? (want > 0 ? want : 1) : cap);
+  kern<<<grid, kBwdWarps * 32, smem, stream>>>(bp);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bwd(const BwdParams& bp, cudaStream_t stream) {
+  switch (bp.k.mlp.Hd / 32) {
+    case 1: return launch_bwd_t<1>(bp, stream);
+    case 2: return launch_bwd_t<2>(bp, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace bts

@@ -319,18 +319,20 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
         const float4* grow = reinterpret_cast<const float4*>(w_gi + lane * kGiStride);
         const float4* wo4 = reinterpret_cast<const float4*>(s_wout);
         if (!big) {
+          float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;   // four independent chains (ILP)
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float4 g = grow[c * 4 + e];
               const float4 wv = wo4[c * 4 + e];
-              logit = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 0]) + g.x, 0.0f), wv.x, logit);
-              logit = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 1]) + g.y, 0.0f), wv.y, logit);
-              logit = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 2]) + g.z, 0.0f), wv.z, logit);
-              logit = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 3]) + g.w, 0.0f), wv.w, logit);
+              l0 = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 0]) + g.x, 0.0f), wv.x, l0);
+              l1 = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 1]) + g.y, 0.0f), wv.y, l1);
+              l2 = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 2]) + g.z, 0.0f), wv.z, l2);
+              l3 = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 3]) + g.w, 0.0f), wv.w, l3);
             }
           }
+          logit += (l0 + l1) + (l2 + l3);
         } else {   // rare: raw-coordinate part of lin_in in fp32
           const float4* wrh = reinterpret_cast<const float4*>(smem + kOffWrawA);   // chunk 0: [hi0 hi1 hi2 hi0]
           const float4* wrl = reinterpret_cast<const float4*>(smem + kOffWrawB);   // chunk 0: [lo0 lo1 lo2 0]; hi+lo = fp32 weight

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BTS_ABI_VERSION 1
+#define BTS_ABI_VERSION 2
 #define BTS_MAX_BLOCKS 8   /* ResnetFC blocks supported by the kernels */
 
 typedef struct CUstream_st* bts_stream_t; /* == cudaStream_t */
@@ -128,6 +128,33 @@ int bts_pack_images(const float* img_nchw, int32_t nv_total, int32_t Cc, int32_t
  * from a counter-based generator keyed by (seed, ray, sample) (the reference draws torch.rand_like, nerf.py:116). */
 int bts_render_fwd(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg* cfg, const float* rays, int64_t n,
                    int64_t R, const float* u_or_null, uint64_t seed, const BtsRenderOut* out, bts_stream_t stream);
+
+/* Upstream gradients of a scalar loss w.r.t. the differentiable outputs of bts_render_fwd (NULL = zero); shapes as
+ * in BtsRenderOut.  invalid / z_samps / rgb_samps do not depend on the trainable tensors. */
+typedef struct {
+  const float* rgb;      /* (n, R, Vc*Cc) */
+  const float* depth;    /* (n, R)        */
+  const float* weights;  /* (n, R, K)     */
+  const float* alphas;   /* (n, R, K)     */
+} BtsRenderGrad;
+
+/* Gradients produced by bts_render_bwd; every buffer is ACCUMULATED into (caller zero-initialises), NULL = skip. */
+typedef struct {
+  float* d_G;        /* (n, H, W, Hd)  gradient of the folded map (bilinear scatter-add)                 */
+  float* d_g_empty;  /* (Hd)                                                                            */
+  float* d_w_pe;     /* (Hd, P)        gradient of lin_in.weight[:, C:] (the positional-code columns)     */
+  float* d_w_out;    /* (Hd)           gradient of lin_out.weight                                         */
+  float* d_b_out;    /* (1)            gradient of lin_out.bias                                           */
+} BtsParamGrad;
+
+/* Backward of bts_render_fwd (what torch autograd does for the reference's op chain during
+ * `loss.backward()`, utils/base_trainer.py:297): recomputes the forward per ray from the same inputs (same `u` or
+ * `seed`), then back-propagates through compositing (nerf.py:283-304), softplus, lin_out and lin_in.  The dense tail
+ * of the chain is the caller's: dF = d_G * W_in[:, :C], dW_in[:, :C] = d_G^T * F (+ d_g_empty x empty_feature),
+ * db_in = sum(d_G) + d_g_empty.  Supports d_hidden <= 64 and n_blocks = 0 (the KITTI training configs). */
+int bts_render_bwd(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg* cfg, const float* rays, int64_t n,
+                   int64_t R, const float* u_or_null, uint64_t seed, const BtsRenderGrad* upstream,
+                   const BtsParamGrad* grads, bts_stream_t stream);
 
 /* Replaces a direct BTSNet.forward(xyz, only_density=...) point query (models_bts.py:266-338; callers
  * scripts/inference_setup.py:214, models/bts/evaluator_lidar.py:305).  xyz (n, P, 3).

@@ -59,6 +59,39 @@ def fixtures():
     return out
 
 
+GRAD_FIXTURES = ("cfg2_small_bias4", "cfg3_small_n2")
+
+
+def probe_loss(coarse):
+    """Deterministic scalar of the differentiable outputs (used for the gradient fixtures and their tests):
+    sum_t <t, sin(0.37 i + phase_t)> over rgb, depth (x0.1), weights, alphas."""
+    total = 0.0
+    for name, phase, scale in (("rgb", 0.1, 1.0), ("depth", 0.2, 0.1), ("weights", 0.3, 1.0), ("alphas", 0.4, 1.0)):
+        t = coarse[name]
+        coef = torch.sin(0.37 * torch.arange(t.numel(), dtype=torch.float32, device=t.device) + phase).view_as(t)
+        total = total + scale * (t * coef).sum()
+    return total
+
+
+def reference_gradients(ref, wl: syn.Workload, sd):
+    """Gradients of probe_loss through the UNMODIFIED reference (torch autograd, like utils/base_trainer.py:297)."""
+    net = ref_import.make_reference_net(ref, wl.model_conf, wl.feats)
+    net.load_state_dict(sd, strict=False)
+    renderer = ref.NeRFRenderer.from_conf(wl.renderer_conf)
+    wrapped = renderer.bind_parallel(net, gpus=None).eval()
+    net.encode(wl.images, wl.Ks, wl.poses_c2w, ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
+    net.set_scale(0)
+    torch.manual_seed(12345)
+    out = wrapped(wl.rays, want_weights=True, want_alphas=True)["coarse"]
+    probe_loss(out).backward()
+    g = {"mlp_coarse.lin_in.weight": net.mlp_coarse.lin_in.weight.grad, "mlp_coarse.lin_in.bias": net.mlp_coarse.lin_in.bias.grad,
+         "mlp_coarse.lin_out.weight": net.mlp_coarse.lin_out.weight.grad, "mlp_coarse.lin_out.bias": net.mlp_coarse.lin_out.bias.grad,
+         "feats": net.encoder.feats.grad}
+    if getattr(net, "learn_empty", False):
+        g["empty_feature"] = net.empty_feature.grad
+    return {k: v.detach().clone() for k, v in g.items()}
+
+
 def run_reference(ref, wl: syn.Workload):
     torch.manual_seed(wl.weight_seed)
     net = ref_import.make_reference_net(ref, wl.model_conf, wl.feats)
@@ -112,6 +145,9 @@ def main():
             arrays["out/" + k] = v
         for k, v in q.items():
             arrays["query/" + k] = v
+        if wl.name in GRAD_FIXTURES:
+            for k, v in reference_gradients(ref, wl, sd).items():
+                arrays["grad/" + k] = v
         meta = {"name": wl.name, "model_conf": wl.model_conf, "renderer_conf": wl.renderer_conf,
                 "ids_encoder": wl.ids_encoder, "ids_render": wl.ids_render,
                 "reference": "Brummi/BehindTheScenes @ /root/reference (unmodified; stubs: dotmap, lpips, omegaconf; "

@@ -18,7 +18,7 @@ def load_golden(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     meta = json.loads(bytes(z["meta"]).decode())
     g = SimpleNamespace(name=name, meta=meta, model_conf=meta["model_conf"], renderer_conf=meta["renderer_conf"],
-                        ids_encoder=meta["ids_encoder"], ids_render=meta["ids_render"], sd={}, out={}, query={})
+                        ids_encoder=meta["ids_encoder"], ids_render=meta["ids_render"], sd={}, out={}, query={}, grad={})
     for k in z.files:
         if k == "meta":
             continue
@@ -29,6 +29,8 @@ def load_golden(name):
             g.out[k[4:]] = t
         elif k.startswith("query/"):
             g.query[k[6:]] = t
+        elif k.startswith("grad/"):
+            g.grad[k[5:]] = t
         else:
             setattr(g, k, t)
     return g

@@ -1,0 +1,37 @@
+"""Gradient helpers shared by the CPU (oracle vs reference fixtures) and GPU (CUDA vs oracle / fixtures) tests."""
+import torch
+
+from oracle import bts_oracle as orc
+from tests.golden_io import mlp_params
+
+GRAD_KEYS = ("mlp_coarse.lin_in.weight", "mlp_coarse.lin_in.bias", "mlp_coarse.lin_out.weight", "mlp_coarse.lin_out.bias",
+             "empty_feature", "feats")
+
+
+def probe_loss(coarse):
+    """Same scalar as oracle/make_goldens.py::probe_loss (the gradient fixtures were produced with it)."""
+    total = 0.0
+    for name, phase, scale in (("rgb", 0.1, 1.0), ("depth", 0.2, 0.1), ("weights", 0.3, 1.0), ("alphas", 0.4, 1.0)):
+        t = coarse[name]
+        coef = torch.sin(0.37 * torch.arange(t.numel(), dtype=torch.float32, device=t.device) + phase).view_as(t)
+        total = total + scale * (t * coef).sum()
+    return total
+
+
+def oracle_gradients(wl, sd):
+    """torch autograd through the oracle port (CPU)."""
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and not k.startswith("code_xyz")}
+    feats = wl.feats.clone().requires_grad_(True)
+    st = orc.encode_state(wl.images, wl.Ks, wl.poses_c2w, feats, wl.ids_encoder, wl.ids_render)
+    fcfg = orc.FieldConfig.from_model_conf(wl.model_conf)
+    rcfg = orc.RenderConfig.from_renderer_conf(wl.renderer_conf)
+    out = orc.render(st, mlp_params(sd), fcfg, rcfg, wl.rays, u=wl.u, empty_feature=sd.get("empty_feature"),
+                     want_weights=True, want_alphas=True)["coarse"]
+    probe_loss(out).backward()
+    g = {k: sd[k].grad for k in GRAD_KEYS if k in sd and sd[k].grad is not None}
+    g["feats"] = feats.grad
+    return g
+
+
+def rel_err(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()

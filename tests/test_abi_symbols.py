@@ -26,7 +26,7 @@ def _declared_functions():
 def test_header_declares_the_expected_entry_points():
     names = _declared_functions()
     for n in ("bts_abi_version", "bts_last_error", "bts_fold_features", "bts_pack_images", "bts_render_fwd",
-              "bts_query_field", "bts_last_kernel"):
+              "bts_query_field", "bts_last_kernel", "bts_render_bwd"):
         assert n in names
 
 
@@ -35,7 +35,7 @@ def test_every_declared_symbol_is_exported(lib):
     for n in _declared_functions():
         assert hasattr(lib, n), f"{n} declared in include/bts_b200.h but not exported"
         assert n in _lib.EXPORTS, f"{n} has no ctypes prototype"
-    assert lib.bts_abi_version() == 1
+    assert lib.bts_abi_version() == 2
     assert lib.bts_last_error() is not None
 
 

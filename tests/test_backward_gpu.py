@@ -1,0 +1,97 @@
+"""GPU: bts_render_bwd (through torch autograd on the drop-in classes) against the gradients of the UNMODIFIED
+reference (fixtures) and against autograd through the oracle at a training-shaped size."""
+import pytest
+import torch
+
+from behindthescenes_b200 import synthetic as syn
+from tests import grad_util as gu
+from tests import parity_util as pu
+from tests.golden_io import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+# fp32 with atomics in a different order + the ulp-level projection sensitivity: relative L2 error
+GRAD_REL_TOL = 2e-3
+
+
+def cuda_gradients(wl, sd, precision=0, use_u=True):
+    net, wrapped = syn.build_model(wl, "cuda", state_dict=sd)
+    wrapped.renderer.precision = precision
+    net.encoder.feats.requires_grad_(True)
+    net.encode(wl.images.cuda(), wl.Ks.cuda(), wl.poses_c2w.cuda(), ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
+    out = wrapped(wl.rays.cuda(), want_weights=True, want_alphas=True, u=wl.u.cuda() if use_u else None)["coarse"]
+    assert out["rgb"].requires_grad and out["depth"].requires_grad and not out["invalid"].requires_grad
+    gu.probe_loss(out).backward()
+    g = {"mlp_coarse.lin_in.weight": net.mlp_coarse.lin_in.weight.grad, "mlp_coarse.lin_in.bias": net.mlp_coarse.lin_in.bias.grad,
+         "mlp_coarse.lin_out.weight": net.mlp_coarse.lin_out.weight.grad, "mlp_coarse.lin_out.bias": net.mlp_coarse.lin_out.bias.grad,
+         "feats": net.encoder.feats.grad}
+    if net.learn_empty:
+        g["empty_feature"] = net.empty_feature.grad
+    return {k: v.detach().cpu() for k, v in g.items()}, {k: v.detach().cpu() for k, v in out.items()}
+
+
+GRAD_FIXTURES = [n for n in golden_names() if load_golden(n).grad]
+
+
+@pytest.mark.parametrize("name", GRAD_FIXTURES)
+def test_backward_matches_reference_gradient_fixture(name):
+    g = load_golden(name)
+    wl = pu.workload_from_golden(g)
+    got, out = cuda_gradients(wl, g.sd)
+    errs = {}
+    for k, ref in g.grad.items():
+        assert got[k].shape == ref.shape, (k, got[k].shape, ref.shape)
+        assert torch.isfinite(got[k]).all(), k
+        errs[k] = gu.rel_err(got[k], ref)
+    print(name, errs)
+    assert max(errs.values()) <= GRAD_REL_TOL, errs
+
+
+def test_backward_training_shape_vs_oracle_autograd():
+    """cfg3-shaped training batch: n=2 frames, 2 colour views, 2048 rays each, K=64, all four upstream gradients."""
+    wl = syn.cfg3_kitti_raw_train(H=48, W=160, n=2, lin_out_bias=-4.0, seed=41, ray_subsample=2048)
+    cpu_net, _ = syn.build_model(wl, "cpu")
+    sd = {k: v.clone() for k, v in cpu_net.state_dict().items() if not k.startswith("encoder.")}
+    got, _ = cuda_gradients(wl, sd)
+    ref = gu.oracle_gradients(wl, sd)
+    errs = {k: gu.rel_err(got[k], ref[k]) for k in ref}
+    print(errs)
+    assert max(errs.values()) <= GRAD_REL_TOL, errs
+
+
+def test_backward_with_in_kernel_jitter_is_consistent():
+    """Without injected u the backward must regenerate the forward's jitter from the saved seed: compare with a
+    finite-difference directional derivative along lin_out.bias (a smooth direction)."""
+    wl = syn.cfg2_kitti360_eval(H=24, W=80, K=64, stereo=True, learn_empty=True, lin_out_bias=-4.0, seed=42, ray_subsample=1024)
+    net, wrapped = syn.build_model(wl, "cuda")
+    net.encode(wl.images.cuda(), wl.Ks.cuda(), wl.poses_c2w.cuda(), ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
+    rays = wl.rays.cuda()
+
+    def loss_at(delta, need_grad):
+        with torch.no_grad():
+            net.mlp_coarse.lin_out.bias.add_(delta)
+        torch.manual_seed(9)                      # same seed -> same in-kernel jitter
+        with torch.set_grad_enabled(need_grad):
+            out = wrapped(rays, want_weights=True, want_alphas=True)["coarse"]
+            l = out["depth"].sum() * 0.01 + out["rgb"].sum()
+        if need_grad:
+            l.backward()
+        with torch.no_grad():
+            net.mlp_coarse.lin_out.bias.sub_(delta)
+        return l.item()
+
+    loss_at(0.0, True)
+    g = net.mlp_coarse.lin_out.bias.grad.item()
+    eps = 1e-2
+    fd = (loss_at(eps, False) - loss_at(-eps, False)) / (2 * eps)
+    print("analytic", g, "finite difference", fd)
+    assert abs(g - fd) <= 2e-2 * max(1.0, abs(fd))
+
+
+def test_backward_unsupported_configs_raise():
+    wl = syn.cfg4_re10k_nvs(H=24, W=36, K=64, ray_subsample=64)      # one ResnetFC block
+    net, wrapped = syn.build_model(wl, "cuda")
+    net.encode(wl.images.cuda(), wl.Ks.cuda(), wl.poses_c2w.cuda(), ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
+    with pytest.raises(NotImplementedError):
+        wrapped(wl.rays.cuda())                                     # parameters require grad -> autograd path -> blocks
+    with torch.no_grad():
+        wrapped(wl.rays.cuda())                                     # inference is fine
