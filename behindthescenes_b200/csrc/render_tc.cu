@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
       const Proj pf = project(vf, X, Y, Z);
       const bool inv_f = pf.invalid;
       const float pv[3] = {pf.u, pf.v, depth_code(cfg, pf)};
-      bool any_empty;
+      bool any_empty, same_block;
       {
         const Taps t = bilinear_taps(pf.u, pf.v, H, W);
         const int p00 = (int)((b * H + t.y0) * (int64_t)W + t.x0);
@@ -171,6 +171,10 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
         a.z = __int_as_float(t.dy * W * 16);
         a.w = __int_as_float((use_empty && inv_f) ? 1 : 0);
         any_empty = __any_sync(0xffffffffu, use_empty && inv_f);
+        // all 32 samples interpolate inside the same 2x2 pixel block (rays through the encoder camera centre: every
+        // sample of the ray projects to the same pixel, only the ulp-level weights differ) -> fetch the block once
+        const int key = p00 * 4 + t.dx * 2 + t.dy;
+        same_block = __all_sync(0xffffffffu, key == __shfl_sync(0xffffffffu, key, 0));
         w.x = t.wx0 * t.wy0; w.y = t.wx1 * t.wy0; w.z = t.wx0 * t.wy1; w.w = t.wx1 * t.wy1;
         w_taps[lane * 2 + 0] = a;
         w_taps[lane * 2 + 1] = w;
@@ -260,7 +264,24 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
       {
         const int hw = lane >> 4, q = lane & 15;
         const float4* G4 = reinterpret_cast<const float4*>(p.scene.G) + q;
-        if (!any_empty) {
+        if (same_block && !any_empty) {
+          const float4 a = w_taps[0];
+          const float4* g00 = G4 + (uint32_t)__float_as_int(a.x);
+          const float4* g10 = g00 + __float_as_int(a.z);
+          const float4 v00 = __ldg(g00), v01 = __ldg(g00 + __float_as_int(a.y));
+          const float4 v10 = __ldg(g10), v11 = __ldg(g10 + __float_as_int(a.y));
+#pragma unroll 4
+          for (int i = 0; i < 16; ++i) {
+            const int s = 2 * i + hw;
+            const float4 w = w_taps[s * 2 + 1];
+            float4 g;
+            g.x = fmaf(v11.x, w.w, fmaf(v10.x, w.z, fmaf(v01.x, w.y, v00.x * w.x)));
+            g.y = fmaf(v11.y, w.w, fmaf(v10.y, w.z, fmaf(v01.y, w.y, v00.y * w.x)));
+            g.z = fmaf(v11.z, w.w, fmaf(v10.z, w.z, fmaf(v01.z, w.y, v00.z * w.x)));
+            g.w = fmaf(v11.w, w.w, fmaf(v10.w, w.z, fmaf(v01.w, w.y, v00.w * w.x)));
+            *reinterpret_cast<float4*>(w_gi + s * kGiStride + q * 4) = g;
+          }
+        } else if (!any_empty) {
 #pragma unroll 4
           for (int i = 0; i < 16; ++i) {
             const int s = 2 * i + hw;
