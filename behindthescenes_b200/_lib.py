@@ -10,7 +10,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libbts_b200.so")
 
 BTS_MAX_BLOCKS = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 _fp = C.POINTER(C.c_float)
 
 
@@ -40,7 +40,13 @@ class BtsRenderCfg(C.Structure):
 
 class BtsRenderOut(C.Structure):
     _fields_ = [("rgb", C.c_void_p), ("depth", C.c_void_p), ("invalid", C.c_void_p), ("weights", C.c_void_p),
-                ("alphas", C.c_void_p), ("z_samps", C.c_void_p), ("rgb_samps", C.c_void_p)]
+                ("alphas", C.c_void_p), ("z_samps", C.c_void_p), ("rgb_samps", C.c_void_p),
+                ("invalid_mass", C.c_void_p), ("depth_z", C.c_void_p)]
+
+
+class BtsRayGen(C.Structure):
+    _fields_ = [("poses_c2w", C.c_void_p), ("K", C.c_void_p), ("v", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("norm_dir", C.c_int32), ("z_near", C.c_float), ("z_far", C.c_float)]
 
 
 class BtsRenderGrad(C.Structure):
@@ -62,6 +68,8 @@ EXPORTS = {
     "bts_pack_images": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "bts_render_fwd": (C.c_int, [C.POINTER(BtsScene), C.POINTER(BtsMlp), C.POINTER(BtsRenderCfg), C.c_void_p,
                                  C.c_int64, C.c_int64, C.c_void_p, C.c_uint64, C.POINTER(BtsRenderOut), C.c_void_p]),
+    "bts_render_views_fwd": (C.c_int, [C.POINTER(BtsScene), C.POINTER(BtsMlp), C.POINTER(BtsRenderCfg), C.POINTER(BtsRayGen),
+                                       C.c_int64, C.c_void_p, C.c_uint64, C.POINTER(BtsRenderOut), C.c_void_p]),
     "bts_render_bwd": (C.c_int, [C.POINTER(BtsScene), C.POINTER(BtsMlp), C.POINTER(BtsRenderCfg), C.c_void_p,
                                  C.c_int64, C.c_int64, C.c_void_p, C.c_uint64, C.POINTER(BtsRenderGrad),
                                  C.POINTER(BtsParamGrad), C.c_void_p]),

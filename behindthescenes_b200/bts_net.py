@@ -241,7 +241,7 @@ class BTSNet(nn.Module):
         return s, keep
 
     def render_rays(self, renderer, rays, u=None, seed=0, want_weights=False, want_alphas=False, want_z_samps=False,
-                    want_rgb_samps=False):
+                    want_rgb_samps=False, **extras):
         """Fused sampling + field + compositing for ``NeRFRenderer.forward`` (coarse pass).
         rays (n,R,8) -> dict of fresh tensors with the reference's shapes (nerf.py:377-401).  When gradients are
         enabled and the MLP / empty feature / encoder features require them, the call is recorded for autograd and
@@ -249,7 +249,7 @@ class BTSNet(nn.Module):
         ``utils/base_trainer.py:297``)."""
         wants = dict(want_weights=want_weights, want_alphas=want_alphas, want_z_samps=want_z_samps,
                      want_rgb_samps=want_rgb_samps)
-        if torch.is_grad_enabled():
+        if torch.is_grad_enabled() and not extras:
             feats = self.grid_f_features[self._scale] if self.grid_f_features is not None else None
             m = self.mlp_coarse
             diff = [feats, m.lin_in.weight, m.lin_in.bias, m.lin_out.weight, m.lin_out.bias,
@@ -263,21 +263,45 @@ class BTSNet(nn.Module):
                 outs = _RenderFunction.apply(self, renderer, rays, u, seed, wants, tuple(keys), diff[0], diff[1], diff[2],
                                              diff[3], diff[4], ef)
                 return dict(zip(keys, outs))
-        return self._render_rays_raw(renderer, rays, u, seed, **wants)
+        if extras and torch.is_grad_enabled() and any(p.requires_grad for p in self.mlp_coarse.parameters()):
+            raise NotImplementedError("the fused-consumer outputs / in-kernel ray generation are inference-only: "
+                                      "call them under torch.no_grad()")
+        return self._render_rays_raw(renderer, rays, u, seed, **wants, **extras)
 
     def _render_rays_raw(self, renderer, rays, u=None, seed=0, want_weights=False, want_alphas=False, want_z_samps=False,
-                         want_rgb_samps=False):
+                         want_rgb_samps=False, want_invalid=True, want_invalid_mass=False, want_depth_z=False, gen=None):
+        """``rays`` (n,R,8), or ``rays=None`` with ``gen = (poses_c2w (n,v,4,4), Ks (n,v,3,3), H, W, z_near, z_far,
+        norm_dir)`` to generate one ray per pixel of every view inside the kernel (bts_render_views_fwd)."""
         lib = _lib.load()
-        rays_d = _dev_f32(rays)
-        self._require_cuda(rays_d)
         scene, keep = self._scene_struct()
         mlp, keep2 = self._mlp_struct()
         cfg, keep3 = self._cfg_struct(renderer)
-        n, R, _ = rays_d.shape
+        if gen is None:
+            rays_d = _dev_f32(rays)
+            self._require_cuda(rays_d)
+            n, R, _ = rays_d.shape
+            dev = rays_d.device
+            if want_depth_z:
+                raise ValueError("depth_z needs in-kernel ray generation (render_views)")
+        else:
+            poses, Ks, gh, gw, g_near, g_far, norm_dir = gen
+            poses_d, Ks_d = _dev_f32(poses), _dev_f32(Ks[..., :3, :3])
+            self._require_cuda(poses_d)
+            n, gv = poses_d.shape[:2]
+            R = gv * gh * gw
+            dev = poses_d.device
+            rg = _lib.BtsRayGen()
+            rg.poses_c2w, rg.K, rg.v, rg.H, rg.W = poses_d.data_ptr(), Ks_d.data_ptr(), gv, gh, gw
+            rg.norm_dir, rg.z_near, rg.z_far = int(norm_dir), float(g_near), float(g_far)
         K, Vc, Cc = cfg.n_coarse, scene.Vc, scene.Cc
-        dev = rays_d.device
         new = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)  # noqa: E731
-        ret = {"rgb": new(n, R, Vc * Cc), "depth": new(n, R), "invalid": new(n, R, K, Vc)}
+        ret = {"rgb": new(n, R, Vc * Cc), "depth": new(n, R)}
+        if want_invalid:
+            ret["invalid"] = new(n, R, K, Vc)
+        if want_invalid_mass:
+            ret["invalid_mass"] = new(n, R, Vc)
+        if want_depth_z:
+            ret["depth_z"] = new(n, R)
         if want_weights:
             ret["weights"] = new(n, R, K)
         if want_alphas:
@@ -295,9 +319,14 @@ class BTSNet(nn.Module):
             if u_d.numel() != n * R * K:
                 raise ValueError(f"u must have n*R*K = {n * R * K} elements, got {u_d.numel()}")
         stream = torch.cuda.current_stream(dev).cuda_stream
-        rc = lib.bts_render_fwd(C.byref(scene), C.byref(mlp), C.byref(cfg), rays_d.data_ptr(), n, R,
-                                None if u_d is None else u_d.data_ptr(), int(seed) & (2 ** 64 - 1), C.byref(out), stream)
-        _lib.check(rc, "bts_render_fwd")
+        if gen is None:
+            rc = lib.bts_render_fwd(C.byref(scene), C.byref(mlp), C.byref(cfg), rays_d.data_ptr(), n, R,
+                                    None if u_d is None else u_d.data_ptr(), int(seed) & (2 ** 64 - 1), C.byref(out), stream)
+            _lib.check(rc, "bts_render_fwd")
+        else:
+            rc = lib.bts_render_views_fwd(C.byref(scene), C.byref(mlp), C.byref(cfg), C.byref(rg), n,
+                                          None if u_d is None else u_d.data_ptr(), int(seed) & (2 ** 64 - 1), C.byref(out), stream)
+            _lib.check(rc, "bts_render_views_fwd")
         return ret
 
 

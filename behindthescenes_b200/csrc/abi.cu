@@ -82,20 +82,24 @@ int bts_pack_images(const float* img_nchw, int32_t nv_total, int32_t Cc, int32_t
   return BTS_OK;
 }
 
-int bts_render_fwd(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg* cfg, const float* rays, int64_t n,
-                   int64_t R, const float* u_or_null, uint64_t seed, const BtsRenderOut* out, bts_stream_t stream) {
+static int render_fwd_common(const char* who, const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg* cfg,
+                             const float* rays, const BtsRayGen* gen, int64_t n, int64_t R, const float* u_or_null,
+                             uint64_t seed, const BtsRenderOut* out, bts_stream_t stream) {
   int rc = check_common(scene, mlp, cfg);
   if (rc != BTS_OK) return rc;
-  if (!rays || !out) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_render_fwd: rays/out is null");
+  if (!out) return fail(BTS_ERR_INVALID_ARGUMENT, "%s: out is null", who);
   if (n != scene->n) return fail(BTS_ERR_INVALID_ARGUMENT, "rays batch %lld != scene.n %d", (long long)n, scene->n);
   if (R < 0) return fail(BTS_ERR_INVALID_ARGUMENT, "R < 0");
   if (cfg->n_coarse < 1 || !cfg->z_steps) return fail(BTS_ERR_INVALID_ARGUMENT, "n_coarse < 1 or z_steps null");
-  if ((out->rgb || out->invalid || out->rgb_samps) && scene->Vc < 1) return fail(BTS_ERR_INVALID_ARGUMENT, "colour outputs requested with Vc=0");
+  if ((out->rgb || out->invalid || out->rgb_samps || out->invalid_mass) && scene->Vc < 1)
+    return fail(BTS_ERR_INVALID_ARGUMENT, "colour outputs requested with Vc=0");
+  if (out->depth_z && !gen) return fail(BTS_ERR_INVALID_ARGUMENT, "depth_z needs in-kernel ray generation (bts_render_views_fwd)");
   if (n * R == 0) return BTS_OK;
   bts::KernelParams p;
   memset(&p, 0, sizeof(p));
   p.scene = *scene; p.mlp = *mlp; p.cfg = *cfg; p.out = *out;
   p.rays = rays; p.u = u_or_null; p.n_items = n * R; p.per_batch = R; p.seed = seed;
+  if (gen) p.gen = *gen;
   p.p_pad = (mlp->P + 3) & ~3;
   cudaError_t e;
   if (cfg->precision != 2 && bts::tc_supported(p)) {
@@ -106,8 +110,22 @@ int bts_render_fwd(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg*
     g_kernel = "general";
     e = bts::launch_general(p, false, reinterpret_cast<cudaStream_t>(stream));
   }
-  if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_render_fwd: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "%s: %s", who, cudaGetErrorString(e));
   return BTS_OK;
+}
+
+int bts_render_fwd(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg* cfg, const float* rays, int64_t n,
+                   int64_t R, const float* u_or_null, uint64_t seed, const BtsRenderOut* out, bts_stream_t stream) {
+  if (!rays) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_render_fwd: rays is null");
+  return render_fwd_common("bts_render_fwd", scene, mlp, cfg, rays, nullptr, n, R, u_or_null, seed, out, stream);
+}
+
+int bts_render_views_fwd(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg* cfg, const BtsRayGen* gen,
+                         int64_t n, const float* u_or_null, uint64_t seed, const BtsRenderOut* out, bts_stream_t stream) {
+  if (!gen || !gen->poses_c2w || !gen->K) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_render_views_fwd: gen / poses / K is null");
+  if (gen->v < 1 || gen->H < 1 || gen->W < 1) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_render_views_fwd: bad view sizes");
+  return render_fwd_common("bts_render_views_fwd", scene, mlp, cfg, nullptr, gen, n, (int64_t)gen->v * gen->H * gen->W,
+                           u_or_null, seed, out, stream);
 }
 
 int bts_render_bwd(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg* cfg, const float* rays, int64_t n,

@@ -17,7 +17,8 @@ struct KernelParams {
   BtsMlp mlp;
   BtsRenderCfg cfg;
   BtsRenderOut out;
-  const float* rays;     // (n*R, 8)            [render]
+  const float* rays;     // (n*R, 8)            [render]; null -> generated from `gen`
+  BtsRayGen gen;         // in-kernel ray generation (rays == null)
   const float* u;        // (n*R, K) or null    [render]
   const float* xyz;      // (n*P, 3)            [query]
   float* q_sigma;        // (n*P)               [query]
@@ -44,6 +45,53 @@ __device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t ray, uint3
   uint32_t h = fmix32((uint32_t)ray ^ (uint32_t)seed);
   h = fmix32(h ^ ((uint32_t)(ray >> 32) * 0x9E3779B1u) ^ (k * 0x85EBCA77u + 0x165667B1u) ^ (uint32_t)(seed >> 32));
   return (float)(h >> 8) * (1.0f / 16777216.0f);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// One ray = [origin, direction, near, far] (models/common/util/util.py:244-273), either read from the caller's tensor
+// (8 lanes load, shuffle-broadcast) or generated from the camera of its pixel.  All lanes return the same values.
+// zfac = z-component of the unit ray in its camera = the distance->z-depth factor of projection_operations.py:4-16.
+// ------------------------------------------------------------------------------------------------------------------
+struct Ray {
+  float o[3], d[3], near_, far_, zfac;
+};
+
+__device__ __forceinline__ float linspace_m1_1(int i, int steps) {   // torch.linspace(-1, 1, steps)[i], float32
+  if (steps == 1) return -1.0f;
+  const float step = 2.0f / (float)(steps - 1);
+  return i < steps / 2 ? -1.0f + step * (float)i : 1.0f - step * (float)(steps - 1 - i);
+}
+
+__device__ __forceinline__ Ray fetch_ray(const KernelParams& p, int64_t ray, int lane) {
+  Ray r;
+  if (p.rays) {
+    const float rv = lane < 8 ? __ldg(p.rays + ray * 8 + lane) : 0.0f;
+    r.o[0] = __shfl_sync(0xffffffffu, rv, 0); r.o[1] = __shfl_sync(0xffffffffu, rv, 1); r.o[2] = __shfl_sync(0xffffffffu, rv, 2);
+    r.d[0] = __shfl_sync(0xffffffffu, rv, 3); r.d[1] = __shfl_sync(0xffffffffu, rv, 4); r.d[2] = __shfl_sync(0xffffffffu, rv, 5);
+    r.near_ = __shfl_sync(0xffffffffu, rv, 6); r.far_ = __shfl_sync(0xffffffffu, rv, 7);
+    r.zfac = 1.0f;
+    return r;
+  }
+  const BtsRayGen& g = p.gen;
+  const int64_t hw = (int64_t)g.H * g.W;
+  const int64_t cam = ray / hw;                 // b * v + view
+  const int pix = (int)(ray - cam * hw);
+  const int y = pix / g.W, x = pix - y * g.W;
+  const float* Kc = g.K + cam * 9;
+  const float* M = g.poses_c2w + cam * 16;
+  const float cx = __fdiv_rn(__fsub_rn(linspace_m1_1(x, g.W), __ldg(Kc + 2)), __ldg(Kc + 0));   // util.py:140-144
+  const float cy = __fdiv_rn(__fsub_rn(linspace_m1_1(y, g.H), __ldg(Kc + 5)), __ldg(Kc + 4));
+  const float nrm = sqrtf(fmaf(cy, cy, cx * cx) + 1.0f);
+  float dx = cx, dy = cy, dz = 1.0f;
+  if (g.norm_dir) { dx = __fdiv_rn(cx, nrm); dy = __fdiv_rn(cy, nrm); dz = __fdiv_rn(1.0f, nrm); }   // util.py:147-148
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    r.d[i] = fmaf(__ldg(M + i * 4 + 2), dz, fmaf(__ldg(M + i * 4 + 1), dy, __ldg(M + i * 4 + 0) * dx));   // util.py:256-258
+    r.o[i] = __ldg(M + i * 4 + 3);
+  }
+  r.near_ = g.z_near; r.far_ = g.z_far;
+  r.zfac = g.norm_dir ? __fdiv_rn(1.0f, nrm) : 1.0f;
+  return r;
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -74,10 +74,9 @@ __global__ void __launch_bounds__(kBwdWarps * 32) render_bwd_kernel(const BwdPar
 
   for (int64_t ray = (int64_t)blockIdx.x * kBwdWarps + warp; ray < p.n_items; ray += (int64_t)gridDim.x * kBwdWarps) {
     const int64_t b = p.scene.n == 1 ? 0 : ray / p.per_batch;
-    const float rv = lane < 8 ? __ldg(p.rays + ray * 8 + lane) : 0.0f;
-    const float ro0 = __shfl_sync(0xffffffffu, rv, 0), ro1 = __shfl_sync(0xffffffffu, rv, 1), ro2 = __shfl_sync(0xffffffffu, rv, 2);
-    const float rd0 = __shfl_sync(0xffffffffu, rv, 3), rd1 = __shfl_sync(0xffffffffu, rv, 4), rd2 = __shfl_sync(0xffffffffu, rv, 5);
-    const float near_ = __shfl_sync(0xffffffffu, rv, 6), far_ = __shfl_sync(0xffffffffu, rv, 7);
+    const Ray ry = fetch_ray(p, ray, lane);
+    const float ro0 = ry.o[0], ro1 = ry.o[1], ro2 = ry.o[2], rd0 = ry.d[0], rd1 = ry.d[1], rd2 = ry.d[2];
+    const float near_ = ry.near_, far_ = ry.far_;
     View vf;
     load_view(vf, p.scene.K_f + b * 9, p.scene.w2c_f + b * 16);
     if (lane < Vc * Cc) w_grgb[lane] = bp.g_rgb ? __ldg(bp.g_rgb + ray * Vc * Cc + lane) : 0.0f;

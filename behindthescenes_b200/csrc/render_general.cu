@@ -34,7 +34,7 @@ __host__ __device__ inline GeneralSmemLayout general_layout(int Hd, int p_pad, i
   L.warp_pe = 0;
   L.warp_taps = p_pad * 32;
   L.warp_rgb = L.warp_taps + 32 * 8;
-  L.warp_floats = L.warp_rgb + kMaxColorViews * 4;
+  L.warp_floats = L.warp_rgb + kMaxColorViews * 4 + kMaxColorViews;
   L.per_warp = o;
   L.total_floats = o + kWarpsPerCta * L.warp_floats;
   return L;
@@ -91,20 +91,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) render_general_kernel(const
   for (int64_t item = (int64_t)blockIdx.x * kWarpsPerCta + warp; item < n_groups;
        item += (int64_t)gridDim.x * kWarpsPerCta) {
     // ---- per-item setup ----
-    float ro[3] = {0, 0, 0}, rd[3] = {0, 0, 0}, near_ = 0, far_ = 0;
+    float ro[3] = {0, 0, 0}, rd[3] = {0, 0, 0}, near_ = 0, far_ = 0, zfac = 1.0f;
     int64_t b;
     if (!kPoints) {
       b = p.scene.n == 1 ? 0 : item / p.per_batch;
-      const float rv = lane < 8 ? __ldg(p.rays + item * 8 + lane) : 0.0f;
-      ro[0] = __shfl_sync(0xffffffffu, rv, 0); ro[1] = __shfl_sync(0xffffffffu, rv, 1);
-      ro[2] = __shfl_sync(0xffffffffu, rv, 2); rd[0] = __shfl_sync(0xffffffffu, rv, 3);
-      rd[1] = __shfl_sync(0xffffffffu, rv, 4); rd[2] = __shfl_sync(0xffffffffu, rv, 5);
-      near_ = __shfl_sync(0xffffffffu, rv, 6); far_ = __shfl_sync(0xffffffffu, rv, 7);
+      const Ray ry = fetch_ray(p, item, lane);
+      ro[0] = ry.o[0]; ro[1] = ry.o[1]; ro[2] = ry.o[2]; rd[0] = ry.d[0]; rd[1] = ry.d[1]; rd[2] = ry.d[2];
+      near_ = ry.near_; far_ = ry.far_; zfac = ry.zfac;
     } else {
       b = 0;  // per-lane batch index below
     }
     float T_carry = 1.0f, depth_part = 0.0f, wsum_part = 0.0f;
-    if (lane < kMaxColorViews * 4) w_rgb[lane] = 0.0f;
+    for (int i = lane; i < kMaxColorViews * 5; i += 32) w_rgb[i] = 0.0f;
     __syncwarp();
 
     float z_ahead = 0.0f;   // depths are produced one chunk ahead (delta needs z[k+1])
@@ -295,7 +293,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) render_general_kernel(const
       __syncwarp();
     }  // chunks
 
-    if (!kPoints) finish_ray(p, lane, item, depth_part, wsum_part, w_rgb);
+    if (!kPoints) finish_ray(p, lane, item, depth_part, wsum_part, w_rgb, zfac);
   }
 }
 

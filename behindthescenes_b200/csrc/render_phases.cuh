@@ -37,12 +37,13 @@ __device__ __forceinline__ float composite_chunk(const KernelParams& p, int lane
 
 // Colour views (models/bts/model/models_bts.py:218-264, :330-334): project the sample into every render view, fetch
 // RGB bilinearly (border clamp), emit invalid = invalid_colour | invalid_feature, reduce weight * colour over the warp
-// into w_rgb[view*4 + c] (lane 0 accumulates).
+// into w_rgb[view*4 + c] (lane 0 accumulates); w_rgb[kMaxColorViews*4 + view] accumulates the invalid mass.
 template <bool kPoints>
 __device__ __forceinline__ void colour_views(const KernelParams& p, int lane, int64_t bl, float X, float Y, float Z,
                                              bool valid, bool inv_f, float wgt, int64_t sample_id, float* w_rgb) {
   const bool want = kPoints ? (p.q_rgb != nullptr || p.q_invalid != nullptr)
-                            : (p.out.rgb != nullptr || p.out.invalid != nullptr || p.out.rgb_samps != nullptr);
+                            : (p.out.rgb != nullptr || p.out.invalid != nullptr || p.out.rgb_samps != nullptr ||
+                               p.out.invalid_mass != nullptr);
   if (!want) return;
   const int Vc = p.scene.Vc, Cc = p.scene.Cc, Hc = p.scene.Hc, Wc = p.scene.Wc;
   for (int v = 0; v < Vc; ++v) {
@@ -74,6 +75,10 @@ __device__ __forceinline__ void colour_views(const KernelParams& p, int lane, in
           if (lane == 0) w_rgb[v * 4 + c] += tot;
         }
       }
+      if (p.out.invalid_mass) {                       // loss.py:107: (invalid * weights).sum(-2)
+        const float tot = warp_sum(wgt * inv);
+        if (lane == 0) w_rgb[kMaxColorViews * 4 + v] += tot;
+      }
     } else if (valid) {
       if (p.q_invalid) p.q_invalid[sample_id * Vc + v] = inv;
       if (p.q_rgb)
@@ -84,12 +89,14 @@ __device__ __forceinline__ void colour_views(const KernelParams& p, int lane, in
 
 // Per-ray outputs after the last chunk: depth, rgb (+ white background, nerf.py:301-304).
 __device__ __forceinline__ void finish_ray(const KernelParams& p, int lane, int64_t ray, float depth_part, float wsum_part,
-                                           const float* w_rgb) {
+                                           const float* w_rgb, float zfac) {
   const int Vc = p.scene.Vc, Cc = p.scene.Cc;
   const float depth = warp_sum(depth_part);
   const float wsum = warp_sum(wsum_part);
   if (lane == 0 && p.out.depth) p.out.depth[ray] = depth;
+  if (lane == 0 && p.out.depth_z) p.out.depth_z[ray] = depth * zfac;
   __syncwarp();
+  if (p.out.invalid_mass && lane < Vc) p.out.invalid_mass[ray * Vc + lane] = w_rgb[kMaxColorViews * 4 + lane];
   if (p.out.rgb && lane < Vc * Cc) {
     float r = w_rgb[(lane / Cc) * 4 + (lane % Cc)];
     if (p.cfg.white_bkgd) r = r + 1.0f - wsum;

@@ -45,7 +45,7 @@ constexpr int kOffWarp = kOffBar + 16;
 constexpr int kWarpTaps = 0;                         // [32][8] floats
 constexpr int kWarpGi = 32 * 8 * 4;                  // [32][68] floats
 constexpr int kWarpRgb = kWarpGi + 32 * kGiStride * 4;
-constexpr int kWarpBytes = kWarpRgb + kMaxColorViews * 4 * 4;
+constexpr int kWarpBytes = kWarpRgb + (kMaxColorViews * 4 + kMaxColorViews) * 4;
 constexpr int kSmemBytes = kOffWarp + 4 * kWarpBytes;
 static_assert(4 * (kSmemBytes + 1024) <= 233472, "4 CTAs per SM must fit the 228 KB shared memory of an SM");
 
@@ -135,12 +135,11 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
     const bool active = ray_raw < n_rays;
     const int64_t ray = active ? ray_raw : n_rays - 1;
     const int64_t b = p.scene.n == 1 ? 0 : ray / p.per_batch;   // 64-bit division only for batched scenes
-    const float rv = lane < 8 ? __ldg(p.rays + ray * 8 + lane) : 0.0f;
-    const float ro0 = __shfl_sync(0xffffffffu, rv, 0), ro1 = __shfl_sync(0xffffffffu, rv, 1), ro2 = __shfl_sync(0xffffffffu, rv, 2);
-    const float rd0 = __shfl_sync(0xffffffffu, rv, 3), rd1 = __shfl_sync(0xffffffffu, rv, 4), rd2 = __shfl_sync(0xffffffffu, rv, 5);
-    const float near_ = __shfl_sync(0xffffffffu, rv, 6), far_ = __shfl_sync(0xffffffffu, rv, 7);
+    const Ray ry = fetch_ray(p, ray, lane);
+    const float ro0 = ry.o[0], ro1 = ry.o[1], ro2 = ry.o[2], rd0 = ry.d[0], rd1 = ry.d[1], rd2 = ry.d[2];
+    const float near_ = ry.near_, far_ = ry.far_;
     float T_carry = 1.0f, depth_part = 0.0f, wsum_part = 0.0f;
-    if (lane < kMaxColorViews * 4) w_rgb[lane] = 0.0f;
+    for (int i = lane; i < kMaxColorViews * 5; i += 32) w_rgb[i] = 0.0f;
     wait_disabled = wait_disabled || (*reinterpret_cast<volatile int*>(&g_tc_barrier_timeouts) != 0);
     View vf;
     load_view(vf, p.scene.K_f + b * 9, p.scene.w2c_f + b * 16);
@@ -384,7 +383,7 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
       colour_views<false>(p, lane, b, X, Y, Z, active, inv_f, wgt, sample_id, w_rgb);
       __syncwarp();
     }
-    if (active) finish_ray(p, lane, ray, depth_part, wsum_part, w_rgb);
+    if (active) finish_ray(p, lane, ray, depth_part, wsum_part, w_rgb, ry.zfac);
     __syncwarp();
   }
 

@@ -67,12 +67,16 @@ class NeRFRenderer(torch.nn.Module):
             self.last_sched += 1
 
     def forward(self, model, rays, want_weights=False, want_alphas=False, want_z_samps=False, want_rgb_samps=False,
-                sample_from_dist=None, u=None):
+                sample_from_dist=None, u=None, **extras):
+        """``extras`` (inference-only extensions): ``want_invalid=False`` drops the (n,R,K,Vc) flag
+        tensor, ``want_invalid_mass=True`` adds ``invalid_mass (n,R,Vc) = sum_k invalid*weights`` (the quantity
+        ``loss.py:105-108`` / ``inference_setup.py:192`` threshold), ``gen=(poses_c2w, Ks, H, W, z_near, z_far,
+        norm_dir)`` with ``rays=None`` generates one ray per pixel in the kernel, ``want_depth_z=True`` adds z-depth."""
         with torch.autograd.profiler.record_function("renderer_forward"):
             if self.sched is not None and self.last_sched.item() > 0:
                 self.n_coarse = self.sched[1][self.last_sched.item() - 1]
                 self.n_fine = self.sched[2][self.last_sched.item() - 1]
-            assert len(rays.shape) == 3
+            assert rays is None or len(rays.shape) == 3
             if self.using_fine or self.n_fine > 0 or sample_from_dist is not None:
                 raise NotImplementedError("fine / importance sampling is not implemented on the B200 render path "
                                           "(every shipped BTS config has n_fine = 0)")
@@ -83,7 +87,7 @@ class NeRFRenderer(torch.nn.Module):
                                 "generic per-point fallback loop")
             seed = int(torch.empty((), dtype=torch.int64).random_().item()) if u is None else 0
             coarse = model.render_rays(self, rays, u=u, seed=seed, want_weights=want_weights, want_alphas=want_alphas,
-                                       want_z_samps=want_z_samps, want_rgb_samps=want_rgb_samps)
+                                       want_z_samps=want_z_samps, want_rgb_samps=want_rgb_samps, **extras)
             return _Out(coarse=_Out(coarse))
 
     def bind_parallel(self, net, gpus=None, simple_output=False):
@@ -99,13 +103,22 @@ class _RenderWrapper(torch.nn.Module):
         self.net, self.renderer, self.simple_output = net, renderer, simple_output
 
     def forward(self, rays, want_weights=False, want_alphas=False, want_z_samps=False, want_rgb_samps=False,
-                sample_from_dist=None, u=None):
-        if rays.shape[0] == 0:   # nerf.py:20-24
+                sample_from_dist=None, u=None, **extras):
+        if rays is not None and rays.shape[0] == 0:   # nerf.py:20-24
             return torch.zeros(0, 3, device=rays.device), torch.zeros(0, device=rays.device)
         so = self.simple_output
         out = self.renderer(self.net, rays, want_weights=want_weights and not so, want_alphas=want_alphas and not so,
                             want_z_samps=want_z_samps and not so, want_rgb_samps=want_rgb_samps and not so,
-                            sample_from_dist=sample_from_dist, u=u)
+                            sample_from_dist=sample_from_dist, u=u, **extras)
         if so:
             return out.coarse.rgb, out.coarse.depth
         return out.toDict()
+
+    def render_views(self, poses_c2w, Ks, height, width, z_near, z_far, norm_dir=True, **kwargs):
+        """One ray per pixel of every given view, generated inside the kernel: replaces
+        ``ImageRaySampler.sample`` + ``util.gen_rays`` + the ``(n, v*H*W, 8)`` ray tensor
+        (``models/bts/model/ray_sampler.py:240-262``, ``models/common/util/util.py:244-273``); ``want_depth_z=True`` also
+        returns the z-depth of ``utils/projection_operations.py:4-16``.  Output shapes are those of ``forward`` with
+        R = v*H*W (ray index = (view*H + y)*W + x, the order ``ImageRaySampler.reconstruct`` expects)."""
+        gen = (poses_c2w, Ks, int(height), int(width), float(z_near), float(z_far), bool(norm_dir))
+        return self.forward(None, gen=gen, **kwargs)

@@ -224,6 +224,8 @@ def run_ours(args):
         net.encode(wl.images.to(dev), wl.Ks.to(dev), wl.poses_c2w.to(dev), ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     wants = dict(want_weights=True, want_alphas=True)
+    metric_buf = torch.zeros(2, device=dev, dtype=torch.float32)     # [sum of depths, ray count]: the per-step scalars
+    metric_buf[1] = float(n_rays)
 
     def one_step(timed, ev=None):
         flush.fill_(1)                                                 # evict L2 (126 MB) -- outside the event pair
@@ -234,11 +236,13 @@ def run_ours(args):
         if ev:
             ev[1].record()
         out = wrapped(rays_dev, **wants)["coarse"]
-        metric = {"depth_sum": out["depth"].sum(), "rays": torch.tensor(float(n_rays), device=dev)}
-        metric = R.allreduce_sums(metric)
+        torch.sum(out["depth"], dim=None, out=metric_buf[0])           # per-rank partial of the step's scalar metric
+        red = metric_buf.clone()
+        if world > 1:
+            dist.all_reduce(red, op=dist.ReduceOp.SUM)                 # the path's only collective (NCCL, 8 bytes)
         if ev:
             ev[2].record()
-        return out, metric
+        return out, {"depth_sum": red[0], "rays": red[1]}
 
     def sync_all():
         if world > 1:
@@ -274,25 +278,43 @@ def run_ours(args):
     kern_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
 
     # ---- end to end through the public API with HOST buffers -----------------------------------------------------------
+    # What the reference's evaluate_step moves to the device per frame (utils/base_evaluator.py:132): images, poses,
+    # intrinsics.  The step: H2D of those (pinned), colour packing + fold of the frame's features (device resident, as
+    # produced by the encoder), rays generated in the kernel from the poses (render_views), D2H of the per-ray result
+    # (z-depth + rgb) -- per-sample tensors stay on the device like in the reference (consumed by its loss/metrics).
+    H_img, W_img = wl.images.shape[-2:]
+    n_views = n_rays // (H_img * W_img)
+    v_frame = wl.poses_c2w.shape[1]
+    img_host = wl.images.contiguous().pin_memory()
+    assert n_views == v_frame, "every rank renders one stereo frame (weak scaling)"
+    poses_host = wl.poses_c2w.contiguous().pin_memory()
+    Ks_host = wl.Ks.contiguous().pin_memory()
+    img_dev = torch.empty_like(img_host, device=dev)
+    poses_dev = torch.empty_like(poses_host, device=dev)
+    Ks_dev = torch.empty_like(Ks_host, device=dev)
     depth_host = torch.empty((1, n_rays), dtype=torch.float32).pin_memory()
     rgb_host = torch.empty((1, n_rays, 3), dtype=torch.float32).pin_memory()
-    rays_stage = torch.empty_like(rays_dev)
     e2e_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
     with torch.no_grad():
         for i in range(-3, args.steps):
             flush.fill_(1)
-            net.invalidate_scene()
             if i >= 0:
                 e2e_ev[i][0].record()
-            rays_stage.copy_(rays_host, non_blocking=True)               # H2D of this step's rays (pinned)
-            o = wrapped(rays_stage, **wants)["coarse"]
-            depth_host.copy_(o["depth"], non_blocking=True)              # D2H of the per-ray result
+            img_dev.copy_(img_host, non_blocking=True)                   # H2D: this frame's images, poses, intrinsics
+            poses_dev.copy_(poses_host, non_blocking=True)
+            Ks_dev.copy_(Ks_host, non_blocking=True)
+            net.grid_c_imgs = (img_dev * 0.5 + 0.5)[:, wl.ids_render]      # encode()'s colour cache (models_bts.py:81,133)
+            net.invalidate_scene()
+            o = wrapped.render_views(poses_dev, Ks_dev, H_img, W_img, wl.model_conf["z_near"], wl.model_conf["z_far"],
+                                     want_depth_z=True, **wants)["coarse"]
+            depth_host.copy_(o["depth_z"], non_blocking=True)            # D2H of the per-ray result
             rgb_host.copy_(o["rgb"], non_blocking=True)
             if i >= 0:
                 e2e_ev[i][1].record()
             torch.cuda.synchronize(dev)
         sync_all()
     e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_ev) / args.steps
+    h2d_bytes = int((img_host.numel() + poses_host.numel() + Ks_host.numel()) * 4)
 
     # ---- max over ranks ----------------------------------------------------------------------------------------------
     t = torch.tensor([step_ms, e2e_ms, kern_ms, prep_ms], device=dev, dtype=torch.float64)
@@ -328,7 +350,7 @@ def run_ours(args):
                            "rays_per_gpu": n_rays, "samples_per_ray": K_SAMPLES, "parallelism": f"ray-shard x{world}",
                            "l2": "256 MiB flush before every timed step", "precision_tier": "exact-fp32" if args.precision == 0 else "fast",
                            "kernel": kernel_name, "ms_fold_pack": prep_ms, "ms_render": render_ms},
-                "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": int(rays_host.numel() * 4),
+                "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": int(depth_host.numel() * 4 + rgb_host.numel() * 4), "ms_per_step": e2e_ms},
                 "gpu_launches": args.steps * (3 + 1),          # fold, fold_empty, pack_images, render per step (ours)
                 "roofline": roof, "clocks": clocks, "wall_s_timed_loop": wall,

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BTS_ABI_VERSION 2
+#define BTS_ABI_VERSION 3
 #define BTS_MAX_BLOCKS 8   /* ResnetFC blocks supported by the kernels */
 
 typedef struct CUstream_st* bts_stream_t; /* == cudaStream_t */
@@ -105,7 +105,23 @@ typedef struct {
   float* alphas;     /* (n, R, K)                                                       */
   float* z_samps;    /* (n, R, K)                                                       */
   float* rgb_samps;  /* (n, R, K, Vc*Cc)                                                */
+  /* fused consumers of the per-sample outputs, all optional:                                  */
+  float* invalid_mass; /* (n, R, Vc)  sum_k invalid[k,v] * weights[k]  -- the "weight guided" invalid test of
+                          models/bts/model/loss.py:105-108 and scripts/inference_setup.py:192 without the (R,K,Vc) tensor */
+  float* depth_z;      /* (n, R)      z-depth = depth * (unit-ray z in its camera), utils/projection_operations.py:4-16;
+                          only with in-kernel ray generation (BtsRayGen)                                            */
 } BtsRenderOut;
+
+/* In-kernel ray generation: replaces ImageRaySampler.sample -> util.gen_rays
+ * (models/bts/model/ray_sampler.py:240-262, models/common/util/util.py:113-149, :244-273): one ray per pixel of every
+ * view, d = R * normalize([(x-cx)/fx, (y-cy)/fy, 1]) with x,y on linspace(-1,1,.), o = t; ray index = ((b*v + view)*H + y)*W + x. */
+typedef struct {
+  const float* poses_c2w; /* (n, v, 4, 4) */
+  const float* K;         /* (n, v, 3, 3) normalised intrinsics */
+  int32_t v, H, W;
+  int32_t norm_dir;       /* util.gen_rays(norm_dir=...) */
+  float z_near, z_far;    /* ray near / far */
+} BtsRayGen;
 
 int bts_abi_version(void);
 const char* bts_last_error(void);
@@ -128,6 +144,10 @@ int bts_pack_images(const float* img_nchw, int32_t nv_total, int32_t Cc, int32_t
  * from a counter-based generator keyed by (seed, ray, sample) (the reference draws torch.rand_like, nerf.py:116). */
 int bts_render_fwd(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg* cfg, const float* rays, int64_t n,
                    int64_t R, const float* u_or_null, uint64_t seed, const BtsRenderOut* out, bts_stream_t stream);
+
+/* Same as bts_render_fwd with the rays generated in the kernel from camera poses (R = gen.v * gen.H * gen.W). */
+int bts_render_views_fwd(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg* cfg, const BtsRayGen* gen,
+                         int64_t n, const float* u_or_null, uint64_t seed, const BtsRenderOut* out, bts_stream_t stream);
 
 /* Upstream gradients of a scalar loss w.r.t. the differentiable outputs of bts_render_fwd (NULL = zero); shapes as
  * in BtsRenderOut.  invalid / z_samps / rgb_samps do not depend on the trainable tensors. */

@@ -26,7 +26,7 @@ def _declared_functions():
 def test_header_declares_the_expected_entry_points():
     names = _declared_functions()
     for n in ("bts_abi_version", "bts_last_error", "bts_fold_features", "bts_pack_images", "bts_render_fwd",
-              "bts_query_field", "bts_last_kernel", "bts_render_bwd"):
+              "bts_query_field", "bts_last_kernel", "bts_render_bwd", "bts_render_views_fwd"):
         assert n in names
 
 
@@ -35,7 +35,7 @@ def test_every_declared_symbol_is_exported(lib):
     for n in _declared_functions():
         assert hasattr(lib, n), f"{n} declared in include/bts_b200.h but not exported"
         assert n in _lib.EXPORTS, f"{n} has no ctypes prototype"
-    assert lib.bts_abi_version() == 2
+    assert lib.bts_abi_version() == 3
     assert lib.bts_last_error() is not None
 
 
@@ -44,7 +44,8 @@ def test_struct_mirrors_match_header_layout():
     # sizes under the LP64 C ABI: int32 fields, 8-byte pointers, natural alignment
     assert ctypes.sizeof(_lib.BtsScene) == 16 + 4 * 8 + 16 + 3 * 8
     assert ctypes.sizeof(_lib.BtsMlp) == 16 + 2 * 8 + 4 * 8 * 8 + 2 * 8
-    assert ctypes.sizeof(_lib.BtsRenderOut) == 7 * 8
+    assert ctypes.sizeof(_lib.BtsRenderOut) == 9 * 8
+    assert ctypes.sizeof(_lib.BtsRayGen) == 2 * 8 + 4 * 4 + 2 * 4
     assert ctypes.sizeof(_lib.BtsRenderCfg) == 9 * 4 + 6 * 4 + 4 + 8 + 8  # 9 ints, 6 floats, pad, ptr, step+precision
 
 

@@ -1,0 +1,64 @@
+"""Training-shaped step (BASELINE config 3 flavour): forward + backward of the render path on patch rays.
+Ours (fused fwd + bts_render_bwd) vs the reference op chain with torch autograd on the same GPU.  Run under gpurun."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from behindthescenes_b200 import synthetic as syn
+from tests import grad_util as gu
+
+n, R = 16, 2048                       # configs/exp_kitti_raw.yaml: batch_size 16, ray_batch_size 2048, patch 8x8
+H, W = 192, 640
+wl = syn.cfg3_kitti_raw_train(H=H, W=W, n=n, lin_out_bias=-4.0, seed=61, ray_subsample=R)
+dev = torch.device("cuda")
+cpu_net, _ = syn.build_model(wl, "cpu")
+sd = {k: v.clone() for k, v in cpu_net.state_dict().items() if not k.startswith("encoder.")}
+net, wrapped = syn.build_model(wl, dev, state_dict=sd)
+net.encoder.feats.requires_grad_(True)
+imgs, Ks, poses, rays, u = (t.to(dev) for t in (wl.images, wl.Ks, wl.poses_c2w, wl.rays, wl.u))
+wants = dict(want_weights=True, want_alphas=True, want_rgb_samps=True)   # models/bts/trainer.py:245
+
+
+def ours():
+    net.zero_grad(set_to_none=True)
+    net.encode(imgs, Ks, poses, ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
+    out = wrapped(rays, u=u, **wants)["coarse"]
+    gu.probe_loss(out).backward()
+
+
+def timeit(fn, steps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+ms_ours = timeit(ours)
+# reference op chain with autograd on the GPU
+from oracle import bts_oracle as orc
+from tests.golden_io import mlp_params
+sdg = {k: v.to(dev).requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and not k.startswith("code_xyz")}
+feats_g = wl.feats.to(dev).requires_grad_(True)
+fcfg = orc.FieldConfig.from_model_conf(wl.model_conf)
+rcfg = orc.RenderConfig.from_renderer_conf(wl.renderer_conf)
+
+
+def ref():
+    for t in list(sdg.values()) + [feats_g]:
+        t.grad = None
+    st = orc.encode_state(imgs, Ks, poses, feats_g, wl.ids_encoder, wl.ids_render)
+    out = orc.render(st, mlp_params(sdg), fcfg, rcfg, rays, u=u, empty_feature=sdg.get("empty_feature"), **wants)["coarse"]
+    gu.probe_loss(out).backward()
+
+
+ms_ref = timeit(ref, steps=5, warm=2)
+g_ours = net.mlp_coarse.lin_in.weight.grad.detach().clone()
+g_ref = sdg["mlp_coarse.lin_in.weight"].grad
+print(json.dumps({"workload": f"cfg3-shaped training step: n={n} frames {H}x{W}, {R} rays each, K=64, Vc=2, fwd+bwd of the render path (encoder excluded)",
+                  "ms_ours": ms_ours, "ms_reference_eager_gpu": ms_ref, "speedup": ms_ref / ms_ours,
+                  "rays_per_s_ours": n * R / ms_ours * 1e3, "grad_rel_err_lin_in": gu.rel_err(g_ours.cpu(), g_ref.cpu())}))
