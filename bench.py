@@ -236,7 +236,9 @@ def run_ours(args):
         if ev:
             ev[1].record()
         out = wrapped(rays_dev, **wants)["coarse"]
-        torch.sum(out["depth"], dim=None, out=metric_buf[0])           # per-rank partial of the step's scalar metric
+        if ev:
+            ev[3].record()
+        metric_buf[0].copy_(out["depth"].sum())                        # per-rank partial of the step's scalar metric
         red = metric_buf.clone()
         if world > 1:
             dist.all_reduce(red, op=dist.ReduceOp.SUM)                 # the path's only collective (NCCL, 8 bytes)
@@ -250,19 +252,19 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     with torch.no_grad():
+        sampler = ClockSampler(local) if rank == 0 else None       # starts sampling now; read after the timed loops
         for _ in range(max(args.warmup, 3)):
             one_step(False)
         sync_all()
-        sampler = ClockSampler(local) if rank == 0 else None
-        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
         t_wall0 = time.perf_counter()
         for i in range(args.steps):
             out, metric = one_step(True, evs[i])
         sync_all()
         wall = time.perf_counter() - t_wall0
-        clocks = sampler.stop() if sampler else None
     prep_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
-    render_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps      # includes the tiny depth-sum + all-reduce
+    render_ms = sum(e[1].elapsed_time(e[3]) for e in evs) / args.steps
+    metric_ms = sum(e[3].elapsed_time(e[2]) for e in evs) / args.steps      # depth-sum + scalar all-reduce
     step_ms = sum(e[0].elapsed_time(e[2]) for e in evs) / args.steps
     kernel_name = lib.bts_last_kernel().decode()
 
@@ -314,6 +316,7 @@ def run_ours(args):
             torch.cuda.synchronize(dev)
         sync_all()
     e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_ev) / args.steps
+    clocks = sampler.stop() if sampler else None                     # covers warm-up, timed loop, kernel loop, e2e loop
     h2d_bytes = int((img_host.numel() + poses_host.numel() + Ks_host.numel()) * 4)
 
     # ---- max over ranks ----------------------------------------------------------------------------------------------
@@ -349,7 +352,7 @@ def run_ours(args):
                 "config": {"workload": "cfg2 KITTI-360 eval_depth: 192x640 stereo frame, 245760 rays/GPU, K=64, outputs rgb+depth+invalid+weights+alphas",
                            "rays_per_gpu": n_rays, "samples_per_ray": K_SAMPLES, "parallelism": f"ray-shard x{world}",
                            "l2": "256 MiB flush before every timed step", "precision_tier": "exact-fp32" if args.precision == 0 else "fast",
-                           "kernel": kernel_name, "ms_fold_pack": prep_ms, "ms_render": render_ms},
+                           "kernel": kernel_name, "ms_fold_pack": prep_ms, "ms_render": render_ms, "ms_metric_allreduce": metric_ms},
                 "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": int(depth_host.numel() * 4 + rgb_host.numel() * 4), "ms_per_step": e2e_ms},
                 "gpu_launches": args.steps * (3 + 1),          # fold, fold_empty, pack_images, render per step (ours)
@@ -387,7 +390,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", type=int, default=0, help="0 exact-fp32 tier, 1 fast tier")
