@@ -10,7 +10,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libbts_b200.so")
 
 BTS_MAX_BLOCKS = 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 _fp = C.POINTER(C.c_float)
 
 
@@ -18,7 +18,7 @@ class BtsScene(C.Structure):
     _fields_ = [("n", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Hd", C.c_int32),
                 ("G", C.c_void_p), ("g_empty", C.c_void_p), ("K_f", C.c_void_p), ("w2c_f", C.c_void_p),
                 ("Vc", C.c_int32), ("Cc", C.c_int32), ("Hc", C.c_int32), ("Wc", C.c_int32),
-                ("img4", C.c_void_p), ("K_c", C.c_void_p), ("w2c_c", C.c_void_p)]
+                ("img4", C.c_void_p), ("K_c", C.c_void_p), ("w2c_c", C.c_void_p), ("same_view_mask", C.c_int32)]
 
 
 class BtsMlp(C.Structure):

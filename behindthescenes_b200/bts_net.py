@@ -107,6 +107,13 @@ class BTSNet(nn.Module):
         self.grid_f_features = [F.interpolate(l, (h_, w_)).view(n, nv, c_l, h_, w_) for l in latents]
         self.grid_f_Ks, self.grid_f_poses_w2c, self.grid_f_combine = Ks[:, ie], w2c[:, ie], None
         self.grid_c_imgs, self.grid_c_Ks, self.grid_c_poses_w2c, self.grid_c_combine = colour_src[:, ir], Ks[:, ir], w2c[:, ir], None
+        # colour views that are the encoder view itself (eval_depth: ids_render == ids_encoder): the kernels reuse the
+        # feature-view projection for them
+        self._same_view_mask = 0
+        if len(ie) == 1:
+            for vi, r in enumerate(ir):
+                if r == ie[0] and vi < 31:
+                    self._same_view_mask |= 1 << vi
         self._encode_gen += 1
         self._scene_cache.clear()
 
@@ -236,6 +243,7 @@ class BTSNet(nn.Module):
         s.K_f, s.w2c_f = Kf.data_ptr(), Mf.data_ptr()
         s.Vc, s.Cc, s.Hc, s.Wc = Vc, Cc, Hc, Wc
         s.img4, s.K_c, s.w2c_c = img4.data_ptr(), Kc.data_ptr(), Mc.data_ptr()
+        s.same_view_mask = int(getattr(self, "_same_view_mask", 0)) if (Hc, Wc) == (H, W) else 0
         keep = [f, w, b_in, G, g_empty, efd, imgs, img4, Kf, Mf, Kc, Mc]
         self._scene_cache["scene"] = (key, s, keep)
         return s, keep

@@ -98,16 +98,18 @@ __device__ __forceinline__ Ray fetch_ray(const KernelParams& p, int64_t ray, int
 // Stratified depth of sample k on a ray (nerf.py:103-123), rounding exactly like the reference's separate
 // elementwise ops (no FMA contraction): steps = linspace[k] + u*step;  lindisp: 1/(1/near*(1-s) + 1/far*s).
 // ------------------------------------------------------------------------------------------------------------------
+// `near_` / `far_` are 1/near, 1/far (rounded once per ray, like the reference's `1 / near` tensors) when lindisp.
 __device__ __forceinline__ float sample_depth(const KernelParams& p, int64_t ray, int k, float near_, float far_) {
   const float uu = p.u ? __ldg(p.u + ray * p.cfg.n_coarse + k) : hash_uniform(p.seed, (uint64_t)ray, (uint32_t)k);
   const float s = __fadd_rn(__ldg(p.cfg.z_steps + k), __fmul_rn(uu, p.cfg.step));
   const float one_m = __fsub_rn(1.0f, s);
-  if (p.cfg.lindisp) {
-    const float a = __fmul_rn(__fdiv_rn(1.0f, near_), one_m);
-    const float b = __fmul_rn(__fdiv_rn(1.0f, far_), s);
-    return __fdiv_rn(1.0f, __fadd_rn(a, b));
-  }
+  if (p.cfg.lindisp) return __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(near_, one_m), __fmul_rn(far_, s)));
   return __fadd_rn(__fmul_rn(near_, one_m), __fmul_rn(far_, s));
+}
+// per-ray bounds in the form sample_depth consumes
+__device__ __forceinline__ void depth_bounds(const KernelParams& p, const Ray& r, float& a, float& b) {
+  a = p.cfg.lindisp ? __fdiv_rn(1.0f, r.near_) : r.near_;
+  b = p.cfg.lindisp ? __fdiv_rn(1.0f, r.far_) : r.far_;
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(kBwdWarps * 32) render_bwd_kernel(const BwdPar
     const int64_t b = p.scene.n == 1 ? 0 : ray / p.per_batch;
     const Ray ry = fetch_ray(p, ray, lane);
     const float ro0 = ry.o[0], ro1 = ry.o[1], ro2 = ry.o[2], rd0 = ry.d[0], rd1 = ry.d[1], rd2 = ry.d[2];
-    const float near_ = ry.near_, far_ = ry.far_;
+    float near_, far_;
+    depth_bounds(p, ry, near_, far_);
     View vf;
     load_view(vf, p.scene.K_f + b * 9, p.scene.w2c_f + b * 16);
     if (lane < Vc * Cc) w_grgb[lane] = bp.g_rgb ? __ldg(bp.g_rgb + ray * Vc * Cc + lane) : 0.0f;

@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) render_general_kernel(const
       b = p.scene.n == 1 ? 0 : item / p.per_batch;
       const Ray ry = fetch_ray(p, item, lane);
       ro[0] = ry.o[0]; ro[1] = ry.o[1]; ro[2] = ry.o[2]; rd[0] = ry.d[0]; rd[1] = ry.d[1]; rd[2] = ry.d[2];
-      near_ = ry.near_; far_ = ry.far_; zfac = ry.zfac;
+      depth_bounds(p, ry, near_, far_);
+      zfac = ry.zfac;
     } else {
       b = 0;  // per-lane batch index below
     }
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) render_general_kernel(const
       }
 
       // ---- phase D: colour views (models_bts.py:218-264, :330-334) ----
-      colour_views<kPoints>(p, lane, bl, X, Y, Z, valid, inv_f, wgt, sample_id, w_rgb);
+      colour_views<kPoints>(p, lane, bl, X, Y, Z, valid, pf, wgt, sample_id, w_rgb);
       __syncwarp();
     }  // chunks
 

@@ -40,16 +40,22 @@ __device__ __forceinline__ float composite_chunk(const KernelParams& p, int lane
 // into w_rgb[view*4 + c] (lane 0 accumulates); w_rgb[kMaxColorViews*4 + view] accumulates the invalid mass.
 template <bool kPoints>
 __device__ __forceinline__ void colour_views(const KernelParams& p, int lane, int64_t bl, float X, float Y, float Z,
-                                             bool valid, bool inv_f, float wgt, int64_t sample_id, float* w_rgb) {
+                                             bool valid, const Proj& pf, float wgt, int64_t sample_id, float* w_rgb) {
+  const bool inv_f = pf.invalid;
   const bool want = kPoints ? (p.q_rgb != nullptr || p.q_invalid != nullptr)
                             : (p.out.rgb != nullptr || p.out.invalid != nullptr || p.out.rgb_samps != nullptr ||
                                p.out.invalid_mass != nullptr);
   if (!want) return;
   const int Vc = p.scene.Vc, Cc = p.scene.Cc, Hc = p.scene.Hc, Wc = p.scene.Wc;
   for (int v = 0; v < Vc; ++v) {
-    View vc;
-    load_view(vc, p.scene.K_c + (bl * Vc + v) * 9, p.scene.w2c_c + (bl * Vc + v) * 16);
-    const Proj pc = project(vc, X, Y, Z);
+    Proj pc;
+    if ((p.scene.same_view_mask >> v) & 1) {
+      pc = pf;                                     // this colour view is the encoder view: same projection, same flags
+    } else {
+      View vc;
+      load_view(vc, p.scene.K_c + (bl * Vc + v) * 9, p.scene.w2c_c + (bl * Vc + v) * 16);
+      pc = project(vc, X, Y, Z);
+    }
     const Taps t = bilinear_taps(pc.u, pc.v, Hc, Wc);
     const float4* base = reinterpret_cast<const float4*>(p.scene.img4) + ((bl * Vc + v) * Hc + t.y0) * (int64_t)Wc + t.x0;
     float col[4] = {0, 0, 0, 0};

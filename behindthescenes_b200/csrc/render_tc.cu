@@ -137,7 +137,8 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
     const int64_t b = p.scene.n == 1 ? 0 : ray / p.per_batch;   // 64-bit division only for batched scenes
     const Ray ry = fetch_ray(p, ray, lane);
     const float ro0 = ry.o[0], ro1 = ry.o[1], ro2 = ry.o[2], rd0 = ry.d[0], rd1 = ry.d[1], rd2 = ry.d[2];
-    const float near_ = ry.near_, far_ = ry.far_;
+    float near_, far_;
+    depth_bounds(p, ry, near_, far_);
     float T_carry = 1.0f, depth_part = 0.0f, wsum_part = 0.0f;
     for (int i = lane; i < kMaxColorViews * 5; i += 32) w_rgb[i] = 0.0f;
     wait_disabled = wait_disabled || (*reinterpret_cast<volatile int*>(&g_tc_barrier_timeouts) != 0);
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
 
       // ---------------- C, D ----------------
       const float wgt = composite_chunk(p, lane, k, K, active, z, z_next, sigma, sample_id, T_carry, depth_part, wsum_part);
-      colour_views<false>(p, lane, b, X, Y, Z, active, inv_f, wgt, sample_id, w_rgb);
+      colour_views<false>(p, lane, b, X, Y, Z, active, pf, wgt, sample_id, w_rgb);
       __syncwarp();
     }
     if (active) finish_ray(p, lane, ray, depth_part, wsum_part, w_rgb, ry.zfac);

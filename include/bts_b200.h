@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BTS_ABI_VERSION 3
+#define BTS_ABI_VERSION 4
 #define BTS_MAX_BLOCKS 8   /* ResnetFC blocks supported by the kernels */
 
 typedef struct CUstream_st* bts_stream_t; /* == cudaStream_t */
@@ -51,6 +51,8 @@ typedef struct {
   const float* img4;    /* (n, Vc, Hc, Wc, 4), values as cached by encode ([0,1])       */
   const float* K_c;     /* (n, Vc, 3, 3)                                                */
   const float* w2c_c;   /* (n, Vc, 4, 4)                                                */
+  int32_t same_view_mask; /* bit v set: colour view v is the encoder view itself (same K, pose, size; eval_depth:
+                             ids_render == ids_encoder) -> its projection and flags are reused, not recomputed */
 } BtsScene;
 
 /* MLP = ResnetFC parameters (models/common/model/resnetfc.py:66-184), d_latent = 0, ReLU, d_out = 1.
