@@ -26,7 +26,7 @@ constexpr int kBwdWarps = 4;
 constexpr int kBwdMaxK = 256;
 
 template <int NU>
-__global__ void __launch_bounds__(kBwdWarps * 32) render_bwd_kernel(const BwdParams bp) {
+__global__ void __launch_bounds__(kBwdWarps * 32, 3) render_bwd_kernel(const BwdParams bp) {
   extern __shared__ __align__(16) float smem[];
   const KernelParams& p = bp.k;
   constexpr int Hd = NU * 32;

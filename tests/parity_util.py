@@ -80,11 +80,16 @@ def compare_render(wl, got, ref, label=""):
     stats["depth_rel_max"] = rel.max().item()
     assert stats["depth_abs_rel"] <= DEPTH_ABS_REL_MEAN, (label, stats)
     assert stats["depth_rel_max"] <= DEPTH_REL_MAX, (label, stats)
+    # Colour samples are a bilinear fetch at ix = (u+1)*W/2: a few-ulp difference in the projected u (different but
+    # equally valid fp32 summation orders in the projection, e.g. MKL vs FMA chain) moves ix by ~2.5e-7*W pixels, and the
+    # synthetic images are white noise (|gradient| ~ 1 per pixel) -> the colour tolerance scales with the image width.
+    W_img = wl.images.shape[-1]
+    colour_tol = max(VALUE_MAX_ABS, 2.5e-7 * W_img)
     for k in ("rgb", "weights", "alphas", "rgb_samps"):
         if k in ref:
             e = (got[k][ok] - ref[k][ok]).abs().max().item()
             stats[k] = e
-            assert e <= VALUE_MAX_ABS, (label, k, e)
+            assert e <= (colour_tol if k in ("rgb", "rgb_samps") else VALUE_MAX_ABS), (label, k, e)
     return stats
 
 

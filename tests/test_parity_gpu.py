@@ -188,3 +188,26 @@ def test_errors_are_loud():
     net2.encode(wl2.images.cuda(), wl2.Ks.cuda(), wl2.poses_c2w.cuda(), ids_encoder=[0, 1], ids_render=[0])
     with pytest.raises(NotImplementedError):
         wrapped2(wl2.rays.cuda())
+
+
+def test_non_default_stream_and_odd_frame_size():
+    """The ABI launches on torch's *current* stream (SURVEY.md §8b "Threading / streams"); KITTI-Raw's full-resolution
+    frame is 370x1226 (not a multiple of anything): 116 MB folded map, rays from two views."""
+    wl = syn.cfg3_kitti_raw_train(H=370, W=1226, n=1, lin_out_bias=-4.0, seed=71, ray_subsample=6000)
+    sd_net, _ = syn.build_model(wl, "cpu")
+    sd = {k: v.clone() for k, v in sd_net.state_dict().items() if not k.startswith("encoder.")}
+    net, wrapped = syn.build_model(wl, "cuda", state_dict=sd)
+    side = torch.cuda.Stream()
+    with torch.no_grad(), torch.cuda.stream(side):
+        net.encode(wl.images.cuda(), wl.Ks.cuda(), wl.poses_c2w.cuda(), ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
+        out = wrapped(wl.rays.cuda(), u=wl.u.cuda(), **ALL)["coarse"]
+    side.synchronize()
+    got = {k: v.cpu() for k, v in out.items()}
+    ref = pu.oracle_render(wl, sd, **ALL)
+    print(pu.compare_render(wl, got, ref, label="370x1226 on a side stream"))
+
+
+def test_batched_scene_n16_patch_rays():
+    """Training-shaped batch: n=16 scenes in one launch (per-ray batch index), 2 colour views."""
+    wl = syn.cfg3_kitti_raw_train(H=24, W=80, n=16, lin_out_bias=-4.0, seed=72, ray_subsample=512)
+    print(_full_size_case(wl, dict(want_weights=True, want_alphas=True, want_rgb_samps=True), -4.0))
