@@ -10,7 +10,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libbts_b200.so")
 
 BTS_MAX_BLOCKS = 8
-ABI_VERSION = 4
+ABI_VERSION = 5
 _fp = C.POINTER(C.c_float)
 
 
@@ -55,7 +55,8 @@ class BtsRenderGrad(C.Structure):
 
 class BtsParamGrad(C.Structure):
     _fields_ = [("d_G", C.c_void_p), ("d_g_empty", C.c_void_p), ("d_w_pe", C.c_void_p), ("d_w_out", C.c_void_p),
-                ("d_b_out", C.c_void_p)]
+                ("d_b_out", C.c_void_p), ("d_fc0_w", C.c_void_p), ("d_fc0_b", C.c_void_p), ("d_fc1_w", C.c_void_p),
+                ("d_fc1_b", C.c_void_p)]
 
 
 EXPORTS = {

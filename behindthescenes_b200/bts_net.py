@@ -262,14 +262,22 @@ class BTSNet(nn.Module):
             m = self.mlp_coarse
             diff = [feats, m.lin_in.weight, m.lin_in.bias, m.lin_out.weight, m.lin_out.bias,
                     self.empty_feature if self.learn_empty else None]
-            if any(t is not None and t.requires_grad for t in diff):
-                if m.n_blocks != 0:
-                    raise NotImplementedError("backward of the B200 render path implements n_blocks = 0")
+            blk = list(m.blocks[0].fc_0.parameters()) + list(m.blocks[0].fc_1.parameters()) if m.n_blocks == 1 else []
+            if any(t is not None and t.requires_grad for t in diff + blk):
+                if not (m.n_blocks == 0 and m.d_hidden <= 64) and not (m.n_blocks == 1 and m.d_hidden == 32):
+                    raise NotImplementedError("backward of the B200 render path implements n_blocks=0 (d_hidden<=64) and "
+                                              "n_blocks=1 with d_hidden=32 (the shipped KITTI / RE10K training configs)")
                 keys = ["rgb", "depth", "invalid"] + [k for k, w in (("weights", want_weights), ("alphas", want_alphas),
                                                                     ("z_samps", want_z_samps), ("rgb_samps", want_rgb_samps)) if w]
                 ef = diff[5] if diff[5] is not None else torch.zeros(0, device=rays.device)
+                if m.n_blocks == 1:
+                    b0 = m.blocks[0]
+                    blk_t = (b0.fc_0.weight, b0.fc_0.bias, b0.fc_1.weight, b0.fc_1.bias)
+                else:
+                    z = torch.zeros(0, device=rays.device)
+                    blk_t = (z, z, z, z)
                 outs = _RenderFunction.apply(self, renderer, rays, u, seed, wants, tuple(keys), diff[0], diff[1], diff[2],
-                                             diff[3], diff[4], ef)
+                                             diff[3], diff[4], ef, *blk_t)
                 return dict(zip(keys, outs))
         if extras and torch.is_grad_enabled() and any(p.requires_grad for p in self.mlp_coarse.parameters()):
             raise NotImplementedError("the fused-consumer outputs / in-kernel ray generation are inference-only: "
@@ -343,11 +351,12 @@ class _RenderFunction(torch.autograd.Function):
     (recompute per ray, scatter into dG) + the dense tail of the fold as two GEMMs."""
 
     @staticmethod
-    def forward(ctx, net, renderer, rays, u, seed, wants, keys, feats, w_in, b_in, w_out, b_out, empty):
+    def forward(ctx, net, renderer, rays, u, seed, wants, keys, feats, w_in, b_in, w_out, b_out, empty, fc0_w, fc0_b, fc1_w, fc1_b):
         with torch.no_grad():
             out = net._render_rays_raw(renderer, rays, u=u, seed=seed, **wants)
         ctx.net, ctx.renderer, ctx.seed, ctx.keys = net, renderer, seed, keys
         ctx.has_u = u is not None
+        ctx.has_block = fc0_w.numel() > 0
         ctx.K = int(renderer.n_coarse)
         ctx.save_for_backward(rays, u if u is not None else rays.new_zeros(0), feats, w_in, empty)
         res = tuple(out[k] for k in keys)
@@ -385,6 +394,11 @@ class _RenderFunction(torch.autograd.Function):
         dbout = torch.zeros((1,), device=dev, dtype=torch.float32)
         pg = _lib.BtsParamGrad()
         pg.d_G, pg.d_g_empty, pg.d_w_pe, pg.d_w_out, pg.d_b_out = (t.data_ptr() for t in (dG, dge, dwpe, dwout, dbout))
+        dblk = (None, None, None, None)
+        if ctx.has_block:
+            dblk = (torch.zeros((Hd, Hd), device=dev), torch.zeros((Hd,), device=dev), torch.zeros((Hd, Hd), device=dev),
+                    torch.zeros((Hd,), device=dev))
+            pg.d_fc0_w, pg.d_fc0_b, pg.d_fc1_w, pg.d_fc1_b = (t.data_ptr() for t in dblk)
         u_d = _dev_f32(u.to(dev)) if ctx.has_u else None
         stream = torch.cuda.current_stream(dev).cuda_stream
         rc = lib.bts_render_bwd(C.byref(scene), C.byref(mlp), C.byref(cfg), rays_d.data_ptr(), n, R,
@@ -404,4 +418,4 @@ class _RenderFunction(torch.autograd.Function):
             d_WF = d_WF + torch.outer(dge, empty.detach())
             d_empty = W_F.t() @ dge
         d_w_in = torch.cat((d_WF, dwpe), dim=1)
-        return (None, None, None, None, None, None, None, d_feats, d_w_in, d_b_in, dwout.view(1, Hd), dbout, d_empty)
+        return (None, None, None, None, None, None, None, d_feats, d_w_in, d_b_in, dwout.view(1, Hd), dbout, d_empty) + dblk

@@ -12,7 +12,7 @@ size_t general_smem_bytes(int Hd, int p_pad, int n_blocks);
 cudaError_t launch_fold(const float* feat, int n, int C, int H, int W, const float* w_in, int ld, const float* b_in, int Hd,
                         const float* empty, float* G, float* g_empty, cudaStream_t stream);
 cudaError_t launch_bwd(const BwdParams& bp, cudaStream_t stream);
-size_t bwd_smem_bytes(int Hd, int p_pad, int K);
+size_t bwd_smem_bytes(int Hd, int p_pad, int K, int n_blocks);
 bool tc_supported(const KernelParams& p);
 cudaError_t launch_tc(const KernelParams& p, cudaStream_t stream);
 int tc_barrier_timeouts();
@@ -136,8 +136,11 @@ int bts_render_bwd(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg*
   if (!rays || !upstream || !grads) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_render_bwd: rays/upstream/grads is null");
   if (n != scene->n) return fail(BTS_ERR_INVALID_ARGUMENT, "rays batch %lld != scene.n %d", (long long)n, scene->n);
   if (cfg->n_coarse < 1 || !cfg->z_steps) return fail(BTS_ERR_INVALID_ARGUMENT, "n_coarse < 1 or z_steps null");
-  if (mlp->n_blocks != 0) return fail(BTS_ERR_UNSUPPORTED, "backward implements n_blocks = 0 (got %d)", mlp->n_blocks);
-  if (mlp->Hd > 64) return fail(BTS_ERR_UNSUPPORTED, "backward implements d_hidden <= 64 (got %d)", mlp->Hd);
+  if (!(mlp->n_blocks == 0 && mlp->Hd <= 64) && !(mlp->n_blocks == 1 && mlp->Hd == 32))
+    return fail(BTS_ERR_UNSUPPORTED, "backward implements n_blocks=0 with d_hidden<=64, or n_blocks=1 with d_hidden=32 (got %d, %d)",
+                mlp->n_blocks, mlp->Hd);
+  if (mlp->n_blocks == 1 && !(grads->d_fc0_w && grads->d_fc0_b && grads->d_fc1_w && grads->d_fc1_b))
+    return fail(BTS_ERR_INVALID_ARGUMENT, "block gradients (d_fc0_*, d_fc1_*) are null");
   if (mlp->P > 40) return fail(BTS_ERR_UNSUPPORTED, "backward implements a code width <= 40 (got %d)", mlp->P);
   if (cfg->n_coarse > 256) return fail(BTS_ERR_UNSUPPORTED, "backward implements K <= 256 (got %d)", cfg->n_coarse);
   if (upstream->rgb && scene->Vc < 1) return fail(BTS_ERR_INVALID_ARGUMENT, "rgb gradient with Vc=0");
@@ -151,6 +154,7 @@ int bts_render_bwd(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg*
   bp.g_rgb = upstream->rgb; bp.g_depth = upstream->depth; bp.g_weights = upstream->weights; bp.g_alphas = upstream->alphas;
   bp.d_G = grads->d_G; bp.d_g_empty = grads->d_g_empty; bp.d_w_pe = grads->d_w_pe; bp.d_w_out = grads->d_w_out;
   bp.d_b_out = grads->d_b_out;
+  bp.d_fc0_w = grads->d_fc0_w; bp.d_fc0_b = grads->d_fc0_b; bp.d_fc1_w = grads->d_fc1_w; bp.d_fc1_b = grads->d_fc1_b;
   const cudaError_t e = bts::launch_bwd(bp, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_render_bwd: %s", cudaGetErrorString(e));
   return BTS_OK;

@@ -16,5 +16,6 @@ struct BwdParams {
   float* d_w_pe;           // (Hd, P)
   float* d_w_out;          // (Hd)
   float* d_b_out;          // (1)
+  float *d_fc0_w, *d_fc0_b, *d_fc1_w, *d_fc1_b;   // block 0 of ResnetFC (n_blocks = 1, d_hidden = 32), nullable
 };
 }  // namespace bts

@@ -25,8 +25,11 @@ namespace bts {
 constexpr int kBwdWarps = 4;
 constexpr int kBwdMaxK = 256;
 
-template <int NU>
-__global__ void __launch_bounds__(kBwdWarps * 32, 3) render_bwd_kernel(const BwdParams bp) {
+// kBlock: one ResnetFC block (resnetfc.py:53-62) between lin_in and lin_out -- the RE10K configuration (d_hidden = 32,
+// NU = 1): h1 = h0 + fc1(relu(fc0(relu(h0)))); lane n owns hidden unit n and row n of the weight gradients.
+template <int NU, bool kBlock>
+__global__ void __launch_bounds__(kBwdWarps * 32, kBlock ? 2 : 3) render_bwd_kernel(const BwdParams bp) {
+  static_assert(!kBlock || NU == 1, "block backward is implemented for d_hidden = 32");
   extern __shared__ __align__(16) float smem[];
   const KernelParams& p = bp.k;
   constexpr int Hd = NU * 32;
@@ -36,7 +39,14 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 3) render_bwd_kernel(const Bwd
   const int Kpad = (K + 31) & ~31;
   float* s_wpe = smem;                       // [Ppad][Hd]
   float* s_wout = s_wpe + Ppad * Hd;         // [Hd]
-  float* wbase = s_wout + Hd + warp * (Ppad * 32 + 32 * 8 + 32 + 5 * Kpad);
+  // block weights: [fc0 | fc0^T | fc1 | fc1^T] (Hd x Hd each) + b0, b1
+  float* s_w0 = s_wout + Hd;
+  float* s_w0t = s_w0 + (kBlock ? Hd * Hd : 0);
+  float* s_w1 = s_w0t + (kBlock ? Hd * Hd : 0);
+  float* s_w1t = s_w1 + (kBlock ? Hd * Hd : 0);
+  float* s_b0 = s_w1t + (kBlock ? Hd * Hd : 0);
+  float* s_b1 = s_b0 + (kBlock ? Hd : 0);
+  float* wbase = s_b1 + (kBlock ? Hd : 0) + warp * (Ppad * 32 + 32 * 8 + 32 + 5 * Kpad);
   float* w_pe = wbase;                       // [Ppad][32]
   float* w_taps = w_pe + Ppad * 32;          // [32][8]
   float* w_grgb = w_taps + 32 * 8;           // [Vc*Cc <= 32]
@@ -53,6 +63,14 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 3) render_bwd_kernel(const Bwd
       s_wpe[i] = j < P ? __ldg(p.mlp.w_in + (size_t)n * ld + p.mlp.C + j) : 0.0f;
     }
     for (int i = threadIdx.x; i < Hd; i += blockDim.x) s_wout[i] = __ldg(p.mlp.w_out + i);
+    if constexpr (kBlock) {
+      for (int i = threadIdx.x; i < Hd * Hd; i += blockDim.x) {
+        const int n = i / Hd, k = i % Hd;
+        const float a = __ldg(p.mlp.fc0_w[0] + i), b = __ldg(p.mlp.fc1_w[0] + i);
+        s_w0[i] = a; s_w0t[k * Hd + n] = a; s_w1[i] = b; s_w1t[k * Hd + n] = b;
+      }
+      for (int i = threadIdx.x; i < Hd; i += blockDim.x) { s_b0[i] = __ldg(p.mlp.fc0_b[0] + i); s_b1[i] = __ldg(p.mlp.fc1_b[0] + i); }
+    }
   }
   __syncthreads();
 
@@ -65,6 +83,9 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 3) render_bwd_kernel(const Bwd
   // persistent per-lane gradient accumulators (this lane's NU hidden units)
   float acc_wpe[NU][40];
   float acc_wout[NU], acc_gempty[NU], acc_bout = 0.0f;
+  float acc_w0[kBlock ? 32 : 1], acc_w1[kBlock ? 32 : 1], acc_b0 = 0.0f, acc_b1 = 0.0f;   // row `lane` of d fc0 / d fc1
+#pragma unroll
+  for (int i = 0; i < (kBlock ? 32 : 1); ++i) { acc_w0[i] = 0.0f; acc_w1[i] = 0.0f; }
 #pragma unroll
   for (int n = 0; n < NU; ++n) {
     acc_wout[n] = 0.0f; acc_gempty[n] = 0.0f;
@@ -147,6 +168,18 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 3) render_bwd_kernel(const Bwd
           for (int ss = 0; ss < 8; ++ss)
 #pragma unroll
             for (int n = 0; n < NU; ++n) acc[ss][n] = fmaf(wv[n], cv[ss], acc[ss][n]);
+        }
+        if constexpr (kBlock) {
+#pragma unroll
+          for (int ss = 0; ss < 8; ++ss) {
+            const float a0 = fmaxf(acc[ss][0], 0.0f);
+            float t = s_b0[lane];
+            for (int i = 0; i < 32; ++i) t = fmaf(s_w0t[i * 32 + lane], __shfl_sync(0xffffffffu, a0, i), t);
+            const float a1 = fmaxf(t, 0.0f);
+            float d = s_b1[lane];
+            for (int i = 0; i < 32; ++i) d = fmaf(s_w1t[i * 32 + lane], __shfl_sync(0xffffffffu, a1, i), d);
+            acc[ss][0] += d;
+          }
         }
 #pragma unroll
         for (int ss = 0; ss < 8; ++ss) {
@@ -276,16 +309,53 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 3) render_bwd_kernel(const Bwd
         }
         // hbar[ss][n] = lbar_s * w_out[n] * [h > 0];   d w_out += lbar * relu(h);  d b_out += lbar
         float hbar[8][NU];
+        if constexpr (kBlock) {
+#pragma unroll 1
+          for (int ss = 0; ss < 8; ++ss) {   // rolled: keeps the 104 gradient accumulators in registers
+            const int ks = c0 + s0 + ss;
+            const float lb = ks < K ? sc_lbar[ks] : 0.0f;
+            if (lane == 0) acc_bout += lb;
+            // recompute the block forward for this sample (lane = unit)
+            const float h0 = acc[ss][0], a0 = fmaxf(h0, 0.0f);
+            float t = s_b0[lane];
+            for (int i = 0; i < 32; ++i) t = fmaf(s_w0t[i * 32 + lane], __shfl_sync(0xffffffffu, a0, i), t);
+            const float a1 = fmaxf(t, 0.0f);
+            float d = s_b1[lane];
+            for (int i = 0; i < 32; ++i) d = fmaf(s_w1t[i * 32 + lane], __shfl_sync(0xffffffffu, a1, i), d);
+            const float h1 = h0 + d;
+            acc_wout[0] = fmaf(lb, fmaxf(h1, 0.0f), acc_wout[0]);
+            const float hb1 = h1 > 0.0f ? lb * s_wout[lane] : 0.0f;          // dL/dh1 (also dL/d d, and the skip path)
+            // fc1: d W1[lane][i] += hb1 * a1_i ; d b1 += hb1 ; dL/da1_i = sum_n W1[n][i] hb1_n
+            acc_b1 += hb1;
+            float ra1 = 0.0f;
 #pragma unroll
-        for (int ss = 0; ss < 8; ++ss) {
-          const int ks = c0 + s0 + ss;
-          const float lb = ks < K ? sc_lbar[ks] : 0.0f;
-          if (lane == 0) acc_bout += lb;
+            for (int i = 0; i < 32; ++i) {
+              acc_w1[i] = fmaf(hb1, __shfl_sync(0xffffffffu, a1, i), acc_w1[i]);
+              ra1 = fmaf(s_w1[i * 32 + lane], __shfl_sync(0xffffffffu, hb1, i), ra1);
+            }
+            const float tb = t > 0.0f ? ra1 : 0.0f;                            // dL/dt
+            // fc0: d W0[lane][i] += tb * a0_i ; d b0 += tb ; dL/da0_i = sum_n W0[n][i] tb_n
+            acc_b0 += tb;
+            float ra0 = 0.0f;
 #pragma unroll
-          for (int n = 0; n < NU; ++n) {
-            const float h = acc[ss][n];
-            acc_wout[n] = fmaf(lb, fmaxf(h, 0.0f), acc_wout[n]);
-            hbar[ss][n] = h > 0.0f ? lb * s_wout[lane * NU + n] : 0.0f;
+            for (int i = 0; i < 32; ++i) {
+              acc_w0[i] = fmaf(tb, __shfl_sync(0xffffffffu, a0, i), acc_w0[i]);
+              ra0 = fmaf(s_w0[i * 32 + lane], __shfl_sync(0xffffffffu, tb, i), ra0);
+            }
+            hbar[ss][0] = hb1 + (h0 > 0.0f ? ra0 : 0.0f);                      // dL/dh0
+          }
+        } else {
+#pragma unroll
+          for (int ss = 0; ss < 8; ++ss) {
+            const int ks = c0 + s0 + ss;
+            const float lb = ks < K ? sc_lbar[ks] : 0.0f;
+            if (lane == 0) acc_bout += lb;
+#pragma unroll
+            for (int n = 0; n < NU; ++n) {
+              const float h = acc[ss][n];
+              acc_wout[n] = fmaf(lb, fmaxf(h, 0.0f), acc_wout[n]);
+              hbar[ss][n] = h > 0.0f ? lb * s_wout[lane * NU + n] : 0.0f;
+            }
           }
         }
         // d W_pe[n][j] += sum_s hbar[s][n] * code[j][s]
@@ -351,17 +421,26 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 3) render_bwd_kernel(const Bwd
       if (j < P && bp.d_w_pe) atomicAdd(bp.d_w_pe + (size_t)unit * P + j, acc_wpe[n][j]);
   }
   if (lane == 0 && bp.d_b_out) atomicAdd(bp.d_b_out, acc_bout);
+  if constexpr (kBlock) {
+    if (bp.d_fc0_w) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { atomicAdd(bp.d_fc0_w + lane * 32 + i, acc_w0[i]); atomicAdd(bp.d_fc1_w + lane * 32 + i, acc_w1[i]); }
+      atomicAdd(bp.d_fc0_b + lane, acc_b0);
+      atomicAdd(bp.d_fc1_b + lane, acc_b1);
+    }
+  }
 }
 
-size_t bwd_smem_bytes(int Hd, int p_pad, int K) {
+size_t bwd_smem_bytes(int Hd, int p_pad, int K, int n_blocks) {
   const int Kpad = (K + 31) & ~31;
-  return (size_t)(p_pad * Hd + Hd + kBwdWarps * (p_pad * 32 + 32 * 8 + 32 + 5 * Kpad)) * sizeof(float);
+  const int blk = n_blocks ? 4 * Hd * Hd + 2 * Hd : 0;
+  return (size_t)(p_pad * Hd + Hd + blk + kBwdWarps * (p_pad * 32 + 32 * 8 + 32 + 5 * Kpad)) * sizeof(float);
 }
 
-template <int NU>
+template <int NU, bool kBlock>
 static cudaError_t launch_bwd_t(const BwdParams& bp, cudaStream_t stream) {
-  const size_t smem = bwd_smem_bytes(NU * 32, bp.k.p_pad, bp.k.cfg.n_coarse);
-  auto kern = render_bwd_kernel<NU>;
+  const size_t smem = bwd_smem_bytes(NU * 32, bp.k.p_pad, bp.k.cfg.n_coarse, kBlock ? 1 : 0);
+  auto kern = render_bwd_kernel<NU, kBlock>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int dev = 0, sms = 148, occ = 1;
@@ -378,9 +457,11 @@ static cudaError_t launch_bwd_t(const BwdParams& bp, cudaStream_t stream) {
 }
 
 cudaError_t launch_bwd(const BwdParams& bp, cudaStream_t stream) {
+  if (bp.k.mlp.n_blocks == 1 && bp.k.mlp.Hd == 32) return launch_bwd_t<1, true>(bp, stream);
+  if (bp.k.mlp.n_blocks != 0) return cudaErrorInvalidValue;
   switch (bp.k.mlp.Hd / 32) {
-    case 1: return launch_bwd_t<1>(bp, stream);
-    case 2: return launch_bwd_t<2>(bp, stream);
+    case 1: return launch_bwd_t<1, false>(bp, stream);
+    case 2: return launch_bwd_t<2, false>(bp, stream);
   }
   return cudaErrorInvalidValue;
 }

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BTS_ABI_VERSION 4
+#define BTS_ABI_VERSION 5
 #define BTS_MAX_BLOCKS 8   /* ResnetFC blocks supported by the kernels */
 
 typedef struct CUstream_st* bts_stream_t; /* == cudaStream_t */
@@ -167,13 +167,18 @@ typedef struct {
   float* d_w_pe;     /* (Hd, P)        gradient of lin_in.weight[:, C:] (the positional-code columns)     */
   float* d_w_out;    /* (Hd)           gradient of lin_out.weight                                         */
   float* d_b_out;    /* (1)            gradient of lin_out.bias                                           */
+  float* d_fc0_w;    /* (Hd, Hd)       blocks.0.fc_0.weight   } only for n_blocks = 1 (RE10K: d_hidden = 32),    */
+  float* d_fc0_b;    /* (Hd)           blocks.0.fc_0.bias     } NULL otherwise                                    */
+  float* d_fc1_w;    /* (Hd, Hd)       blocks.0.fc_1.weight                                                       */
+  float* d_fc1_b;    /* (Hd)           blocks.0.fc_1.bias                                                         */
 } BtsParamGrad;
 
 /* Backward of bts_render_fwd (what torch autograd does for the reference's op chain during
  * `loss.backward()`, utils/base_trainer.py:297): recomputes the forward per ray from the same inputs (same `u` or
  * `seed`), then back-propagates through compositing (nerf.py:283-304), softplus, lin_out and lin_in.  The dense tail
  * of the chain is the caller's: dF = d_G * W_in[:, :C], dW_in[:, :C] = d_G^T * F (+ d_g_empty x empty_feature),
- * db_in = sum(d_G) + d_g_empty.  Supports d_hidden <= 64 and n_blocks = 0 (the KITTI training configs). */
+ * db_in = sum(d_G) + d_g_empty.  Supports n_blocks = 0 with d_hidden <= 64 (the KITTI training configs) and
+ * n_blocks = 1 with d_hidden = 32 (the RE10K training config). */
 int bts_render_bwd(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg* cfg, const float* rays, int64_t n,
                    int64_t R, const float* u_or_null, uint64_t seed, const BtsRenderGrad* upstream,
                    const BtsParamGrad* grads, bts_stream_t stream);

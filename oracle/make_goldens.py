@@ -59,7 +59,7 @@ def fixtures():
     return out
 
 
-GRAD_FIXTURES = ("cfg2_small_bias4", "cfg3_small_n2")
+GRAD_FIXTURES = ("cfg2_small_bias4", "cfg3_small_n2", "cfg4_small")
 
 
 def probe_loss(coarse):
@@ -89,6 +89,10 @@ def reference_gradients(ref, wl: syn.Workload, sd):
          "feats": net.encoder.feats.grad}
     if getattr(net, "learn_empty", False):
         g["empty_feature"] = net.empty_feature.grad
+    for bi, blk in enumerate(net.mlp_coarse.blocks):
+        for nm, prm in (("fc_0.weight", blk.fc_0.weight), ("fc_0.bias", blk.fc_0.bias), ("fc_1.weight", blk.fc_1.weight),
+                        ("fc_1.bias", blk.fc_1.bias)):
+            g[f"mlp_coarse.blocks.{bi}.{nm}"] = prm.grad
     return {k: v.detach().clone() for k, v in g.items()}
 
 

@@ -28,7 +28,7 @@ def oracle_gradients(wl, sd):
     out = orc.render(st, mlp_params(sd), fcfg, rcfg, wl.rays, u=wl.u, empty_feature=sd.get("empty_feature"),
                      want_weights=True, want_alphas=True)["coarse"]
     probe_loss(out).backward()
-    g = {k: sd[k].grad for k in GRAD_KEYS if k in sd and sd[k].grad is not None}
+    g = {k: sd[k].grad for k in sd if k != "feats" and sd[k].grad is not None}
     g["feats"] = feats.grad
     return g
 

@@ -26,6 +26,10 @@ def cuda_gradients(wl, sd, precision=0, use_u=True):
          "feats": net.encoder.feats.grad}
     if net.learn_empty:
         g["empty_feature"] = net.empty_feature.grad
+    for bi, blk in enumerate(net.mlp_coarse.blocks):
+        for nm, prm in (("fc_0.weight", blk.fc_0.weight), ("fc_0.bias", blk.fc_0.bias), ("fc_1.weight", blk.fc_1.weight),
+                        ("fc_1.bias", blk.fc_1.bias)):
+            g[f"mlp_coarse.blocks.{bi}.{nm}"] = prm.grad
     return {k: v.detach().cpu() for k, v in g.items()}, {k: v.detach().cpu() for k, v in out.items()}
 
 
@@ -88,7 +92,8 @@ def test_backward_with_in_kernel_jitter_is_consistent():
 
 
 def test_backward_unsupported_configs_raise():
-    wl = syn.cfg4_re10k_nvs(H=24, W=36, K=64, ray_subsample=64)      # one ResnetFC block
+    wl = syn.cfg4_re10k_nvs(H=24, W=36, K=64, ray_subsample=64)      # one ResnetFC block ...
+    wl.model_conf["mlp_coarse"]["d_hidden"] = 64                    # ... at d_hidden = 64: inference only
     net, wrapped = syn.build_model(wl, "cuda")
     net.encode(wl.images.cuda(), wl.Ks.cuda(), wl.poses_c2w.cuda(), ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
     with pytest.raises(NotImplementedError):
