@@ -397,8 +397,10 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
 
 bool tc_supported(const KernelParams& p) {
   const BtsRenderCfg& c = p.cfg;
+  const int64_t pixels = (int64_t)p.scene.n * p.scene.H * p.scene.W;
   return p.mlp.Hd == 64 && p.mlp.n_blocks == 0 && p.mlp.P == 39 && c.num_freqs == 6 && c.include_input &&
-         c.n_coarse % 32 == 0 && p.scene.Vc <= kMaxColorViews;
+         c.n_coarse % 32 == 0 && p.scene.Vc <= kMaxColorViews &&
+         pixels * 16 < (int64_t)0x7fffffff;   // tap offsets are 32-bit (float4 units)
 }
 
 cudaError_t launch_tc(const KernelParams& p, cudaStream_t stream) {
