@@ -62,6 +62,16 @@ __device__ __forceinline__ float linspace_m1_1(int i, int steps) {   // torch.li
   return i < steps / 2 ? -1.0f + step * (float)i : 1.0f - step * (float)(steps - 1 - i);
 }
 
+// lanes 0..7 hold the 8 floats of a ray tensor row (prefetched by the caller) -> broadcast
+__device__ __forceinline__ Ray ray_from_lanes(float rv) {
+  Ray r;
+  r.o[0] = __shfl_sync(0xffffffffu, rv, 0); r.o[1] = __shfl_sync(0xffffffffu, rv, 1); r.o[2] = __shfl_sync(0xffffffffu, rv, 2);
+  r.d[0] = __shfl_sync(0xffffffffu, rv, 3); r.d[1] = __shfl_sync(0xffffffffu, rv, 4); r.d[2] = __shfl_sync(0xffffffffu, rv, 5);
+  r.near_ = __shfl_sync(0xffffffffu, rv, 6); r.far_ = __shfl_sync(0xffffffffu, rv, 7);
+  r.zfac = 1.0f;
+  return r;
+}
+
 __device__ __forceinline__ Ray fetch_ray(const KernelParams& p, int64_t ray, int lane) {
   Ray r;
   if (p.rays) {

@@ -75,15 +75,24 @@ __device__ __forceinline__ void colour_views(const KernelParams& p, int lane, in
         if (p.out.rgb_samps)
           for (int c = 0; c < Cc; ++c) p.out.rgb_samps[(sample_id * Vc + v) * Cc + c] = col[c];
       }
-      if (p.out.rgb) {
-        for (int c = 0; c < Cc; ++c) {
-          const float tot = warp_sum(wgt * col[c]);   // nerf.py:298
-          if (lane == 0) w_rgb[v * 4 + c] += tot;
+      if (p.out.rgb || p.out.invalid_mass) {
+        // five interleaved butterflies (independent chains): weight * (r, g, b, a) and weight * invalid (loss.py:107)
+        float r0 = wgt * col[0], r1 = wgt * col[1], r2 = wgt * col[2], r3 = wgt * col[3], r4 = wgt * inv;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          r0 += __shfl_xor_sync(0xffffffffu, r0, o);   // nerf.py:298
+          r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+          r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+          if (Cc > 3) r3 += __shfl_xor_sync(0xffffffffu, r3, o);
+          if (p.out.invalid_mass) r4 += __shfl_xor_sync(0xffffffffu, r4, o);
         }
-      }
-      if (p.out.invalid_mass) {                       // loss.py:107: (invalid * weights).sum(-2)
-        const float tot = warp_sum(wgt * inv);
-        if (lane == 0) w_rgb[kMaxColorViews * 4 + v] += tot;
+        if (lane == 0) {
+          if (p.out.rgb) {
+            w_rgb[v * 4 + 0] += r0; w_rgb[v * 4 + 1] += r1; w_rgb[v * 4 + 2] += r2;
+            if (Cc > 3) w_rgb[v * 4 + 3] += r3;
+          }
+          if (p.out.invalid_mass) w_rgb[kMaxColorViews * 4 + v] += r4;
+        }
       }
     } else if (valid) {
       if (p.q_invalid) p.q_invalid[sample_id * Vc + v] = inv;

@@ -130,20 +130,26 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
 
   const int64_t n_rays = p.n_items;
   const int64_t n_pass = (n_rays + 3) / 4;
+  View vf;
+  load_view(vf, p.scene.K_f, p.scene.w2c_f);          // batch element 0; reloaded per ray only for batched scenes
+  // the ray tensor row of the next pass is loaded one pass ahead (its latency hides behind a whole pass)
+  auto ray_of = [&](int64_t pass) { const int64_t r = pass * 4 + warp; return r < n_rays ? r : n_rays - 1; };
+  float rv_next = (p.rays && lane < 8 && (int64_t)blockIdx.x < n_pass) ? __ldg(p.rays + ray_of(blockIdx.x) * 8 + lane) : 0.0f;
   for (int64_t pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
     const int64_t ray_raw = pass * 4 + warp;
     const bool active = ray_raw < n_rays;
     const int64_t ray = active ? ray_raw : n_rays - 1;
     const int64_t b = p.scene.n == 1 ? 0 : ray / p.per_batch;   // 64-bit division only for batched scenes
-    const Ray ry = fetch_ray(p, ray, lane);
+    const float rv = rv_next;
+    if (p.rays && lane < 8 && pass + gridDim.x < n_pass) rv_next = __ldg(p.rays + ray_of(pass + gridDim.x) * 8 + lane);
+    const Ray ry = p.rays ? ray_from_lanes(rv) : fetch_ray(p, ray, lane);
     const float ro0 = ry.o[0], ro1 = ry.o[1], ro2 = ry.o[2], rd0 = ry.d[0], rd1 = ry.d[1], rd2 = ry.d[2];
     float near_, far_;
     depth_bounds(p, ry, near_, far_);
     float T_carry = 1.0f, depth_part = 0.0f, wsum_part = 0.0f;
     for (int i = lane; i < kMaxColorViews * 5; i += 32) w_rgb[i] = 0.0f;
     wait_disabled = wait_disabled || (*reinterpret_cast<volatile int*>(&g_tc_barrier_timeouts) != 0);
-    View vf;
-    load_view(vf, p.scene.K_f + b * 9, p.scene.w2c_f + b * 16);
+    if (p.scene.n != 1) load_view(vf, p.scene.K_f + b * 9, p.scene.w2c_f + b * 16);
 
     float z_ahead = sample_depth(p, ray, lane, near_, far_);   // depths are produced one chunk ahead (delta needs z[k+1])
     for (int c0 = 0; c0 < K; c0 += 32) {
