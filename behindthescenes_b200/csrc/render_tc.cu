@@ -1,5 +1,6 @@
-// Tensor-core render kernel for the flagship BTS configuration (d_hidden = 64, n_blocks = 0, 6-octave code with
-// include_input, K a multiple of 32): the positional-code part of lin_in runs on the 5th-gen tensor cores
+// Tensor-core render kernel for the BTS configurations without ResnetFC blocks (d_hidden = 64 -- the KITTI configs --
+// or 128 -- the BASELINE stress shape; n_blocks = 0, 6-octave code with include_input, K a multiple of 32):
+// the positional-code part of lin_in runs on the 5th-gen tensor cores
 // (tcgen05.mma, accumulator in TMEM), everything else on the CUDA cores, all fused per ray.
 //
 // CTA = 4 warps; each warp owns one ray per pass; a pass is processed in K/32 sub-tiles of 128 samples
@@ -30,24 +31,32 @@ __device__ int g_tc_barrier_timeouts = 0;   // bug guard: bounded mbarrier waits
 namespace tcr {
 
 constexpr int kThreads = 128;
-constexpr uint32_t kColD = 0, kColAhi = 64, kColAlo = 88, kColAraw = 112, kTmemCols = 128;
-constexpr int kGiStride = 68;   // floats per interpolated row in shared memory (64 + 4: conflict-free both ways)
 
-// shared-memory map (bytes)
-constexpr int kOffW16hi = 0;                    // [6 chunks][64 rows][16 B]  fp16, K-major no-swizzle
-constexpr int kOffW16lo = kOffW16hi + 6 * 64 * 16;
-constexpr int kOffWrawA = kOffW16lo + 6 * 64 * 16;   // [2][64][16 B] tf32: [hi0 hi1 hi2 hi0 | hi1 hi2 0 0]
-constexpr int kOffWrawB = kOffWrawA + 2 * 64 * 16;   //               tf32: [lo0 lo1 lo2 0 | 0 0 0 0]
-constexpr int kOffWout = kOffWrawB + 2 * 64 * 16;    // 64 floats
-constexpr int kOffGempty = kOffWout + 256;           // 64 floats
-constexpr int kOffBar = kOffGempty + 256;            // mbarrier (8 B) + tmem base (4 B) + pad
-constexpr int kOffWarp = kOffBar + 16;
-constexpr int kWarpTaps = 0;                         // [32][8] floats
-constexpr int kWarpGi = 32 * 8 * 4;                  // [32][68] floats
-constexpr int kWarpRgb = kWarpGi + 32 * kGiStride * 4;
-constexpr int kWarpBytes = kWarpRgb + (kMaxColorViews * 4 + kMaxColorViews) * 4;
-constexpr int kSmemBytes = kOffWarp + 4 * kWarpBytes;
-static_assert(4 * (kSmemBytes + 1024) <= 233472, "4 CTAs per SM must fit the 228 KB shared memory of an SM");
+// Per-width layout: TMEM columns [D: HD][A16hi: 24][A16lo: 24][Araw: 8], shared-memory map (bytes).
+template <int HD>
+struct L {
+  static_assert(HD == 64 || HD == 128, "tensor-core kernel: d_hidden 64 or 128");
+  static constexpr uint32_t kColD = 0, kColAhi = HD, kColAlo = HD + 24, kColAraw = HD + 48;
+  static constexpr uint32_t kTmemCols = HD == 64 ? 128 : 256;
+  static constexpr int kCtasPerSm = HD == 64 ? 4 : 2;          // 512 TMEM columns per SM
+  static constexpr int kLanesPerSample = HD / 4;               // one float4 (4 channels) per lane in the gather
+  static constexpr int kSamplesPerIter = 32 / kLanesPerSample;
+  static constexpr int kGiStride = HD + 4;                     // floats per interpolated row (+4: conflict-free both ways)
+  static constexpr int kOffW16hi = 0;                          // [6 chunks][HD rows][16 B]  fp16, K-major no-swizzle
+  static constexpr int kOffW16lo = kOffW16hi + 6 * HD * 16;
+  static constexpr int kOffWrawA = kOffW16lo + 6 * HD * 16;    // [2][HD][16 B] tf32: [hi0 hi1 hi2 hi0 | hi1 hi2 0 0]
+  static constexpr int kOffWrawB = kOffWrawA + 2 * HD * 16;    //               tf32: [lo0 lo1 lo2 0 | 0 0 0 0]
+  static constexpr int kOffWout = kOffWrawB + 2 * HD * 16;     // HD floats
+  static constexpr int kOffGempty = kOffWout + HD * 4;         // HD floats
+  static constexpr int kOffBar = kOffGempty + HD * 4;          // mbarrier (8 B) + tmem base (4 B) + pad
+  static constexpr int kOffWarp = kOffBar + 16;
+  static constexpr int kWarpTaps = 0;                          // [32][8] floats
+  static constexpr int kWarpGi = 32 * 8 * 4;                   // [32][HD + 4] floats
+  static constexpr int kWarpRgb = kWarpGi + 32 * kGiStride * 4;
+  static constexpr int kWarpBytes = kWarpRgb + (kMaxColorViews * 4 + kMaxColorViews) * 4;
+  static constexpr int kSmemBytes = kOffWarp + 4 * kWarpBytes;
+  static_assert(kCtasPerSm * (kSmemBytes + 1024) <= 233472, "resident CTAs must fit the 228 KB shared memory of an SM");
+};
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
@@ -62,8 +71,14 @@ __device__ __forceinline__ void split_h2(float s, float c, uint32_t& hi, uint32_
 }
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
-template <bool kExact>
-__global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelParams p) {
+template <int HD, bool kExact>
+__global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_tc_kernel(const KernelParams p) {
+  using Lt = L<HD>;
+  constexpr uint32_t kColD = Lt::kColD, kColAhi = Lt::kColAhi, kColAlo = Lt::kColAlo, kColAraw = Lt::kColAraw, kTmemCols = Lt::kTmemCols;
+  constexpr int kOffW16hi = Lt::kOffW16hi, kOffW16lo = Lt::kOffW16lo, kOffWrawA = Lt::kOffWrawA, kOffWrawB = Lt::kOffWrawB;
+  constexpr int kOffWout = Lt::kOffWout, kOffGempty = Lt::kOffGempty, kOffBar = Lt::kOffBar, kOffWarp = Lt::kOffWarp;
+  constexpr int kWarpTaps = Lt::kWarpTaps, kWarpGi = Lt::kWarpGi, kWarpRgb = Lt::kWarpRgb, kWarpBytes = Lt::kWarpBytes;
+  constexpr int kGiStride = Lt::kGiStride, kLPS = Lt::kLanesPerSample, kSPI = Lt::kSamplesPerIter;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kOffBar);
@@ -79,7 +94,7 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
   const int C = p.mlp.C, ld = C + p.mlp.P;
 
   // ---- one-time setup: weights -> B operands (fp16 hi/lo, tf32 hi/lo), TMEM allocation, mbarrier ----
-  for (int i = tid; i < 64 * 48; i += kThreads) {
+  for (int i = tid; i < HD * 48; i += kThreads) {
     const int n = i / 48, c = i % 48;
     float w = 0.0f;
     if (c < 36) {   // A column c = (d*6 + i)*2 + sc  <->  reference code index 3 + i*6 + sc*3 + d (code.py:39-41)
@@ -88,12 +103,11 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
     }
     const __half hi = __float2half_rn(w);
     const __half lo = __float2half_rn(w - __half2float(hi));
-    const int off = ((c >> 3) * 64 + n) * 16 + (c & 7) * 2;
+    const int off = ((c >> 3) * HD + n) * 16 + (c & 7) * 2;
     *reinterpret_cast<__half*>(smem + kOffW16hi + off) = hi;
     *reinterpret_cast<__half*>(smem + kOffW16lo + off) = lo;
   }
-  if (tid < 64) {
-    const int n = tid;
+  for (int n = tid; n < HD; n += kThreads) {
     float hi[3], lo[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -101,10 +115,10 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
       hi[d] = tf32_hi(w);
       lo[d] = w - hi[d];
     }
-    *reinterpret_cast<float4*>(smem + kOffWrawA + (0 * 64 + n) * 16) = make_float4(hi[0], hi[1], hi[2], hi[0]);
-    *reinterpret_cast<float4*>(smem + kOffWrawA + (1 * 64 + n) * 16) = make_float4(hi[1], hi[2], 0.f, 0.f);
-    *reinterpret_cast<float4*>(smem + kOffWrawB + (0 * 64 + n) * 16) = make_float4(lo[0], lo[1], lo[2], 0.f);
-    *reinterpret_cast<float4*>(smem + kOffWrawB + (1 * 64 + n) * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(smem + kOffWrawA + (0 * HD + n) * 16) = make_float4(hi[0], hi[1], hi[2], hi[0]);
+    *reinterpret_cast<float4*>(smem + kOffWrawA + (1 * HD + n) * 16) = make_float4(hi[1], hi[2], 0.f, 0.f);
+    *reinterpret_cast<float4*>(smem + kOffWrawB + (0 * HD + n) * 16) = make_float4(lo[0], lo[1], lo[2], 0.f);
+    *reinterpret_cast<float4*>(smem + kOffWrawB + (1 * HD + n) * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
     s_wout[n] = __ldg(p.mlp.w_out + n);
     s_gempty[n] = p.scene.g_empty ? __ldg(p.scene.g_empty + n) : 0.0f;
   }
@@ -126,7 +140,7 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
   const int H = p.scene.H, W = p.scene.W;
   const float b_out = __ldg(p.mlp.b_out);
   const bool use_empty = cfg.learn_empty && p.scene.g_empty != nullptr;
-  const uint32_t idesc16 = tc::instr_desc(tc::kFmtF16, 128, 64), idesc32 = tc::instr_desc(tc::kFmtTF32, 128, 64);
+  const uint32_t idesc16 = tc::instr_desc(tc::kFmtF16, 128, HD), idesc32 = tc::instr_desc(tc::kFmtTF32, 128, HD);
 
   const int64_t n_rays = p.n_items;
   const int64_t n_pass = (n_rays + 3) / 4;
@@ -172,9 +186,9 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
         const Taps t = bilinear_taps(pf.u, pf.v, H, W);
         const int p00 = (int)((b * H + t.y0) * (int64_t)W + t.x0);
         float4 a, w;
-        a.x = __int_as_float(p00 * 16);                 // in float4 units of a 64-channel pixel
-        a.y = __int_as_float(t.dx * 16);
-        a.z = __int_as_float(t.dy * W * 16);
+        a.x = __int_as_float(p00 * (HD / 4));           // in float4 units of an HD-channel pixel
+        a.y = __int_as_float(t.dx * (HD / 4));
+        a.z = __int_as_float(t.dy * W * (HD / 4));
         a.w = __int_as_float((use_empty && inv_f) ? 1 : 0);
         any_empty = __any_sync(0xffffffffu, use_empty && inv_f);
         // all 32 samples interpolate inside the same 2x2 pixel block (rays through the encoder camera centre: every
@@ -251,25 +265,26 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
         const uint32_t sW = tc::smem_u32(smem);
 #pragma unroll
         for (int ks = 0; ks < 3; ++ks) {
-          const uint64_t bhi = tc::smem_desc_kmajor_noswizzle(sW + kOffW16hi + ks * 2 * 64 * 16, 64 * 16, 128);
+          const uint64_t bhi = tc::smem_desc_kmajor_noswizzle(sW + kOffW16hi + ks * 2 * HD * 16, HD * 16, 128);
           tc::mma_f16_ts(tmem + kColD, tmem + kColAhi + ks * 8, bhi, idesc16, ks > 0);
           if (kExact) {
-            const uint64_t blo = tc::smem_desc_kmajor_noswizzle(sW + kOffW16lo + ks * 2 * 64 * 16, 64 * 16, 128);
+            const uint64_t blo = tc::smem_desc_kmajor_noswizzle(sW + kOffW16lo + ks * 2 * HD * 16, HD * 16, 128);
             tc::mma_f16_ts(tmem + kColD, tmem + kColAlo + ks * 8, bhi, idesc16, 1);
             tc::mma_f16_ts(tmem + kColD, tmem + kColAhi + ks * 8, blo, idesc16, 1);
           }
         }
-        tc::mma_tf32_ts(tmem + kColD, tmem + kColAraw, tc::smem_desc_kmajor_noswizzle(sW + kOffWrawA, 64 * 16, 128), idesc32, 1);
+        tc::mma_tf32_ts(tmem + kColD, tmem + kColAraw, tc::smem_desc_kmajor_noswizzle(sW + kOffWrawA, HD * 16, 128), idesc32, 1);
         if (kExact)
-          tc::mma_tf32_ts(tmem + kColD, tmem + kColAraw, tc::smem_desc_kmajor_noswizzle(sW + kOffWrawB, 64 * 16, 128), idesc32, 1);
+          tc::mma_tf32_ts(tmem + kColD, tmem + kColAraw, tc::smem_desc_kmajor_noswizzle(sW + kOffWrawB, HD * 16, 128), idesc32, 1);
         tc::mma_commit(bar);
       }
       __syncwarp();
 
-      // ---------------- P2: coalesced bilinear gather of G, half-warp per sample ----------------
+      // ---------------- P2: coalesced bilinear gather of G: HD/4 lanes per sample, one 16-byte load per lane and tap ----
       {
-        const int hw = lane >> 4, q = lane & 15;
+        const int hw = lane / kLPS, q = lane % kLPS;
         const float4* G4 = reinterpret_cast<const float4*>(p.scene.G) + q;
+        constexpr int kIters = 32 / kSPI;
         if (same_block && !any_empty) {
           const float4 a = w_taps[0];
           const float4* g00 = G4 + (uint32_t)__float_as_int(a.x);
@@ -277,8 +292,8 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
           const float4 v00 = __ldg(g00), v01 = __ldg(g00 + __float_as_int(a.y));
           const float4 v10 = __ldg(g10), v11 = __ldg(g10 + __float_as_int(a.y));
 #pragma unroll 4
-          for (int i = 0; i < 16; ++i) {
-            const int s = 2 * i + hw;
+          for (int i = 0; i < kIters; ++i) {
+            const int s = kSPI * i + hw;
             const float4 w = w_taps[s * 2 + 1];
             float4 g;
             g.x = fmaf(v11.x, w.w, fmaf(v10.x, w.z, fmaf(v01.x, w.y, v00.x * w.x)));
@@ -289,8 +304,8 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
           }
         } else if (!any_empty) {
 #pragma unroll 4
-          for (int i = 0; i < 16; ++i) {
-            const int s = 2 * i + hw;
+          for (int i = 0; i < kIters; ++i) {
+            const int s = kSPI * i + hw;
             const float4 a = w_taps[s * 2 + 0];
             const float4 w = w_taps[s * 2 + 1];
             const float4* g00 = G4 + (uint32_t)__float_as_int(a.x);
@@ -306,8 +321,8 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
           }
         } else {   // some samples of this chunk left the encoder frustum: they take the learned empty row
 #pragma unroll 2
-          for (int i = 0; i < 16; ++i) {
-            const int s = 2 * i + hw;
+          for (int i = 0; i < kIters; ++i) {
+            const int s = kSPI * i + hw;
             const float4 a = w_taps[s * 2 + 0];
             const float4 w = w_taps[s * 2 + 1];
             float4 g;
@@ -338,13 +353,14 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
       bar_phase ^= 1u;
       tc::tc_fence_after_sync();
       float logit = b_out;
-      {
+#pragma unroll
+      for (int grp = 0; grp < HD / 64; ++grp) {      // 64 accumulator columns at a time (register budget)
         uint32_t dv[4][16];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tc::tmem_ld_x16(t_lane + kColD + c * 16, dv[c]);
+        for (int c = 0; c < 4; ++c) tc::tmem_ld_x16(t_lane + kColD + grp * 64 + c * 16, dv[c]);
         tc::tmem_ld_wait();
-        const float4* grow = reinterpret_cast<const float4*>(w_gi + lane * kGiStride);
-        const float4* wo4 = reinterpret_cast<const float4*>(s_wout);
+        const float4* grow = reinterpret_cast<const float4*>(w_gi + lane * kGiStride + grp * 64);
+        const float4* wo4 = reinterpret_cast<const float4*>(s_wout + grp * 64);
         if (!big) {
           float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;   // four independent chains (ILP)
 #pragma unroll
@@ -361,8 +377,8 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
           }
           logit += (l0 + l1) + (l2 + l3);
         } else {   // rare: raw-coordinate part of lin_in in fp32
-          const float4* wrh = reinterpret_cast<const float4*>(smem + kOffWrawA);   // chunk 0: [hi0 hi1 hi2 hi0]
-          const float4* wrl = reinterpret_cast<const float4*>(smem + kOffWrawB);   // chunk 0: [lo0 lo1 lo2 0]; hi+lo = fp32 weight
+          const float4* wrh = reinterpret_cast<const float4*>(smem + kOffWrawA) + grp * 64;   // chunk 0: [hi0 hi1 hi2 hi0]
+          const float4* wrl = reinterpret_cast<const float4*>(smem + kOffWrawB) + grp * 64;   // chunk 0: [lo0 lo1 lo2 0]; hi+lo = fp32 weight
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
 #pragma unroll
@@ -404,28 +420,35 @@ __global__ void __launch_bounds__(kThreads, 4) render_tc_kernel(const KernelPara
 bool tc_supported(const KernelParams& p) {
   const BtsRenderCfg& c = p.cfg;
   const int64_t pixels = (int64_t)p.scene.n * p.scene.H * p.scene.W;
-  return p.mlp.Hd == 64 && p.mlp.n_blocks == 0 && p.mlp.P == 39 && c.num_freqs == 6 && c.include_input &&
-         c.n_coarse % 32 == 0 && p.scene.Vc <= kMaxColorViews &&
-         pixels * 16 < (int64_t)0x7fffffff;   // tap offsets are 32-bit (float4 units)
+  return (p.mlp.Hd == 64 || p.mlp.Hd == 128) && p.mlp.n_blocks == 0 && p.mlp.P == 39 && c.num_freqs == 6 &&
+         c.include_input && c.n_coarse % 32 == 0 && p.scene.Vc <= kMaxColorViews &&
+         pixels * (p.mlp.Hd / 4) < (int64_t)0x7fffffff;   // tap offsets are 32-bit (float4 units)
 }
 
-cudaError_t launch_tc(const KernelParams& p, cudaStream_t stream) {
-  auto kern = p.cfg.precision == 0 ? tcr::render_tc_kernel<true> : tcr::render_tc_kernel<false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tcr::kSmemBytes);
+template <int HD, bool kExact>
+static cudaError_t launch_tc_t(const KernelParams& p, cudaStream_t stream) {
+  using Lt = tcr::L<HD>;
+  auto kern = tcr::render_tc_kernel<HD, kExact>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Lt::kSmemBytes);
   if (e != cudaSuccess) return e;
-  // 4 CTAs/SM by design (128 regs x 128 threads, 56 KB smem, 128 of 512 TMEM columns each): ask for the full
-  // shared-memory carve-out, otherwise the default split leaves room for a single CTA.
+  // kCtasPerSm CTAs/SM by design (registers, shared memory, TMEM columns): ask for the full shared-memory carve-out,
+  // otherwise the default split leaves room for a single CTA.
   e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int occ = 4;
   const int64_t n_pass = (p.n_items + 3) / 4;
-  const int64_t cap = (int64_t)sms * occ;                 // persistent: every CTA resident, strided over passes
+  const int64_t cap = (int64_t)sms * Lt::kCtasPerSm;      // persistent: every CTA resident, strided over passes
   const int grid = (int)(n_pass < cap ? n_pass : cap);
-  kern<<<grid, tcr::kThreads, tcr::kSmemBytes, stream>>>(p);
+  kern<<<grid, tcr::kThreads, Lt::kSmemBytes, stream>>>(p);
   return cudaGetLastError();
+}
+
+cudaError_t launch_tc(const KernelParams& p, cudaStream_t stream) {
+  const bool exact = p.cfg.precision == 0;
+  if (p.mlp.Hd == 64) return exact ? launch_tc_t<64, true>(p, stream) : launch_tc_t<64, false>(p, stream);
+  return exact ? launch_tc_t<128, true>(p, stream) : launch_tc_t<128, false>(p, stream);
 }
 
 int tc_barrier_timeouts() {

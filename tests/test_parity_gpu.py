@@ -113,6 +113,7 @@ def test_stress_width128_K256_vs_oracle():
     wl = syn.cfg2_kitti360_eval(H=48, W=160, K=256, stereo=True, learn_empty=False, lin_out_bias=-4.0, seed=15, ray_subsample=2048)
     wl.model_conf["mlp_coarse"]["d_hidden"] = 128
     print(_full_size_case(wl, dict(want_weights=True), -4.0))
+    assert _last_kernel() == "tc"                       # the 128-wide variant of the tensor-core kernel
 
 
 def test_ragged_K_and_empty_rays():

@@ -47,4 +47,14 @@ ms = timed(lambda: net(grid, only_density=True), steps=20)
 res["point_query_only_density(256x64x256)"] = {"ms": ms, "points_per_s": grid.shape[1] / ms * 1e3}
 ms = timed(lambda: net(grid), steps=20)
 res["point_query_full(256x64x256)"] = {"ms": ms, "points_per_s": grid.shape[1] / ms * 1e3}
+# BASELINE config 5 shape on a ray subset: d_hidden = 128, K = 256 (random rays against a 192x640 map)
+wl5 = syn.cfg5_stress(R=262144, K=256, d_hidden=128)
+net5, wrapped5 = syn.build_model(wl5, dev)
+with torch.no_grad():
+    net5.encode(wl5.images.to(dev), wl5.Ks.to(dev), wl5.poses_c2w.to(dev), ids_encoder=wl5.ids_encoder, ids_render=wl5.ids_render)
+rays5 = wl5.rays.to(dev)
+for name, prec in (("stress_Hd128_K256_tc_exact", 0), ("stress_Hd128_K256_general", 2)):
+    wrapped5.renderer.precision = prec
+    ms = timed(lambda: wrapped5(rays5, want_invalid=False), steps=5, warm=2)
+    res[name] = {"ms": ms, "rays_per_s": rays5.shape[1] / ms * 1e3, "samples_per_s": rays5.shape[1] * 256 / ms * 1e3}
 print(json.dumps(res))
