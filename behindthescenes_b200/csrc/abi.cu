@@ -14,7 +14,7 @@ cudaError_t launch_fold(const float* feat, int n, int C, int H, int W, const flo
 cudaError_t launch_bwd(const BwdParams& bp, cudaStream_t stream);
 size_t bwd_smem_bytes(int Hd, int p_pad, int K, int n_blocks);
 bool tc_supported(const KernelParams& p);
-cudaError_t launch_tc(const KernelParams& p, cudaStream_t stream);
+cudaError_t launch_tc(const KernelParams& p, bool points, cudaStream_t stream);
 int tc_barrier_timeouts();
 cudaError_t launch_pack_images(const float* img, int nv_total, int Cc, int Hc, int Wc, float* out, cudaStream_t stream);
 }  // namespace bts
@@ -104,7 +104,7 @@ static int render_fwd_common(const char* who, const BtsScene* scene, const BtsMl
   cudaError_t e;
   if (cfg->precision != 2 && bts::tc_supported(p)) {
     g_kernel = "tc";
-    e = bts::launch_tc(p, reinterpret_cast<cudaStream_t>(stream));
+    e = bts::launch_tc(p, false, reinterpret_cast<cudaStream_t>(stream));
   } else {
     if (cfg->precision == 1) return fail(BTS_ERR_UNSUPPORTED, "fast tier needs the tensor-core kernel (Hd=64, n_blocks=0, 6-octave code, K%%32==0)");
     g_kernel = "general";
@@ -175,7 +175,14 @@ int bts_query_field(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg
   p.xyz = xyz; p.q_sigma = sigma; p.q_invalid_f = invalid_f; p.q_rgb = rgb_or_null; p.q_invalid = invalid_or_null;
   p.n_items = n * P; p.per_batch = P;
   p.p_pad = (mlp->P + 3) & ~3;
-  const cudaError_t e = bts::launch_general(p, true, reinterpret_cast<cudaStream_t>(stream));
+  cudaError_t e;
+  if (cfg->precision != 2 && bts::tc_supported(p)) {
+    g_kernel = "tc";
+    e = bts::launch_tc(p, true, reinterpret_cast<cudaStream_t>(stream));
+  } else {
+    g_kernel = "general";
+    e = bts::launch_general(p, true, reinterpret_cast<cudaStream_t>(stream));
+  }
   if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_query_field: %s", cudaGetErrorString(e));
   return BTS_OK;
 }

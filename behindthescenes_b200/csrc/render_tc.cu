@@ -71,7 +71,9 @@ __device__ __forceinline__ void split_h2(float s, float c, uint32_t& hi, uint32_
 }
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
-template <int HD, bool kExact>
+// kPoints: point-query entry (BTSNet.forward on explicit xyz, models_bts.py:266-338): a pass is 128 points (lane = point),
+// the same P1/MMA/P2/P3, no compositing.
+template <int HD, bool kExact, bool kPoints>
 __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_tc_kernel(const KernelParams p) {
   using Lt = L<HD>;
   constexpr uint32_t kColD = Lt::kColD, kColAhi = Lt::kColAhi, kColAlo = Lt::kColAlo, kColAraw = Lt::kColAraw, kTmemCols = Lt::kTmemCols;
@@ -142,42 +144,61 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_tc_kernel(
   const bool use_empty = cfg.learn_empty && p.scene.g_empty != nullptr;
   const uint32_t idesc16 = tc::instr_desc(tc::kFmtF16, 128, HD), idesc32 = tc::instr_desc(tc::kFmtTF32, 128, HD);
 
-  const int64_t n_rays = p.n_items;
-  const int64_t n_pass = (n_rays + 3) / 4;
+  const int64_t n_rays = p.n_items;                       // rays, or points in the query variant
+  const int64_t n_pass = kPoints ? (n_rays + 127) / 128 : (n_rays + 3) / 4;
   View vf;
   load_view(vf, p.scene.K_f, p.scene.w2c_f);          // batch element 0; reloaded per ray only for batched scenes
   // the ray tensor row of the next pass is loaded one pass ahead (its latency hides behind a whole pass)
   auto ray_of = [&](int64_t pass) { const int64_t r = pass * 4 + warp; return r < n_rays ? r : n_rays - 1; };
-  float rv_next = (p.rays && lane < 8 && (int64_t)blockIdx.x < n_pass) ? __ldg(p.rays + ray_of(blockIdx.x) * 8 + lane) : 0.0f;
+  float rv_next = (!kPoints && p.rays && lane < 8 && (int64_t)blockIdx.x < n_pass) ? __ldg(p.rays + ray_of(blockIdx.x) * 8 + lane) : 0.0f;
   for (int64_t pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
-    const int64_t ray_raw = pass * 4 + warp;
-    const bool active = ray_raw < n_rays;
-    const int64_t ray = active ? ray_raw : n_rays - 1;
-    const int64_t b = p.scene.n == 1 ? 0 : ray / p.per_batch;   // 64-bit division only for batched scenes
-    const float rv = rv_next;
-    if (p.rays && lane < 8 && pass + gridDim.x < n_pass) rv_next = __ldg(p.rays + ray_of(pass + gridDim.x) * 8 + lane);
-    const Ray ry = p.rays ? ray_from_lanes(rv) : fetch_ray(p, ray, lane);
-    const float ro0 = ry.o[0], ro1 = ry.o[1], ro2 = ry.o[2], rd0 = ry.d[0], rd1 = ry.d[1], rd2 = ry.d[2];
-    float near_, far_;
-    depth_bounds(p, ry, near_, far_);
+    // ---- per-pass setup: one ray per warp (render) or one point per lane (query) ----
+    bool active;
+    int64_t ray = 0, b = 0;
+    float ro0 = 0, ro1 = 0, ro2 = 0, rd0 = 0, rd1 = 0, rd2 = 0, near_ = 0, far_ = 0, zfac = 1.0f;
+    float PX = 0, PY = 0, PZ = 0;
+    if constexpr (!kPoints) {
+      const int64_t ray_raw = pass * 4 + warp;
+      active = ray_raw < n_rays;
+      ray = active ? ray_raw : n_rays - 1;
+      b = p.scene.n == 1 ? 0 : ray / p.per_batch;   // 64-bit division only for batched scenes
+      const float rv = rv_next;
+      if (p.rays && lane < 8 && pass + gridDim.x < n_pass) rv_next = __ldg(p.rays + ray_of(pass + gridDim.x) * 8 + lane);
+      const Ray ry = p.rays ? ray_from_lanes(rv) : fetch_ray(p, ray, lane);
+      ro0 = ry.o[0]; ro1 = ry.o[1]; ro2 = ry.o[2]; rd0 = ry.d[0]; rd1 = ry.d[1]; rd2 = ry.d[2];
+      zfac = ry.zfac;
+      depth_bounds(p, ry, near_, far_);
+    } else {
+      const int64_t idx_raw = pass * 128 + warp * 32 + lane;
+      active = idx_raw < n_rays;
+      ray = active ? idx_raw : n_rays - 1;          // "ray" = flat point index in this variant
+      b = p.scene.n == 1 ? 0 : ray / p.per_batch;
+      PX = __ldg(p.xyz + ray * 3 + 0); PY = __ldg(p.xyz + ray * 3 + 1); PZ = __ldg(p.xyz + ray * 3 + 2);
+    }
     float T_carry = 1.0f, depth_part = 0.0f, wsum_part = 0.0f;
     for (int i = lane; i < kMaxColorViews * 5; i += 32) w_rgb[i] = 0.0f;
     wait_disabled = wait_disabled || (*reinterpret_cast<volatile int*>(&g_tc_barrier_timeouts) != 0);
     if (p.scene.n != 1) load_view(vf, p.scene.K_f + b * 9, p.scene.w2c_f + b * 16);
 
-    float z_ahead = sample_depth(p, ray, lane, near_, far_);   // depths are produced one chunk ahead (delta needs z[k+1])
-    for (int c0 = 0; c0 < K; c0 += 32) {
+    float z_ahead = kPoints ? 0.0f : sample_depth(p, ray, lane, near_, far_);   // depths are produced one chunk ahead
+    const int Kloop = kPoints ? 32 : K;
+    for (int c0 = 0; c0 < Kloop; c0 += 32) {
       const int k = c0 + lane;
-      const int64_t sample_id = ray * K + k;
+      const int64_t sample_id = kPoints ? ray : ray * K + k;
       // ---------------- P1: per-sample scalar work, A operand -> TMEM ----------------
-      const float z = z_ahead;
-      z_ahead = (c0 + 32 < K) ? sample_depth(p, ray, k + 32, near_, far_) : 0.0f;
-      float z_next = __shfl_down_sync(0xffffffffu, z, 1);
-      const float z_first_of_next = __shfl_sync(0xffffffffu, z_ahead, 0);
-      if (lane == 31) z_next = z_first_of_next;
-      const float X = __fadd_rn(ro0, __fmul_rn(z, rd0));   // nerf.py:231
-      const float Y = __fadd_rn(ro1, __fmul_rn(z, rd1));
-      const float Z = __fadd_rn(ro2, __fmul_rn(z, rd2));
+      float z = 0.0f, z_next = 0.0f, X, Y, Z;
+      if constexpr (!kPoints) {
+        z = z_ahead;
+        z_ahead = (c0 + 32 < K) ? sample_depth(p, ray, k + 32, near_, far_) : 0.0f;
+        z_next = __shfl_down_sync(0xffffffffu, z, 1);
+        const float z_first_of_next = __shfl_sync(0xffffffffu, z_ahead, 0);
+        if (lane == 31) z_next = z_first_of_next;
+        X = __fadd_rn(ro0, __fmul_rn(z, rd0));   // nerf.py:231
+        Y = __fadd_rn(ro1, __fmul_rn(z, rd1));
+        Z = __fadd_rn(ro2, __fmul_rn(z, rd2));
+      } else {
+        X = PX; Y = PY; Z = PZ;
+      }
       const Proj pf = project(vf, X, Y, Z);
       const bool inv_f = pf.invalid;
       const float pv[3] = {pf.u, pf.v, depth_code(cfg, pf)};
@@ -402,11 +423,21 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_tc_kernel(
       __syncwarp();                        // w_taps / w_gi are rewritten by the next sub-tile
 
       // ---------------- C, D ----------------
-      const float wgt = composite_chunk(p, lane, k, K, active, z, z_next, sigma, sample_id, T_carry, depth_part, wsum_part);
-      colour_views<false>(p, lane, b, X, Y, Z, active, pf, wgt, sample_id, w_rgb);
+      if constexpr (!kPoints) {
+        const float wgt = composite_chunk(p, lane, k, K, active, z, z_next, sigma, sample_id, T_carry, depth_part, wsum_part);
+        colour_views<false>(p, lane, b, X, Y, Z, active, pf, wgt, sample_id, w_rgb);
+      } else {
+        if (active) {
+          p.q_sigma[sample_id] = sigma;
+          p.q_invalid_f[sample_id] = inv_f ? 1.0f : 0.0f;
+        }
+        colour_views<true>(p, lane, b, X, Y, Z, active, pf, 0.0f, sample_id, w_rgb);
+      }
       __syncwarp();
     }
-    if (active) finish_ray(p, lane, ray, depth_part, wsum_part, w_rgb, ry.zfac);
+    if constexpr (!kPoints) {
+      if (active) finish_ray(p, lane, ray, depth_part, wsum_part, w_rgb, zfac);
+    }
     __syncwarp();
   }
 
@@ -421,14 +452,14 @@ bool tc_supported(const KernelParams& p) {
   const BtsRenderCfg& c = p.cfg;
   const int64_t pixels = (int64_t)p.scene.n * p.scene.H * p.scene.W;
   return (p.mlp.Hd == 64 || p.mlp.Hd == 128) && p.mlp.n_blocks == 0 && p.mlp.P == 39 && c.num_freqs == 6 &&
-         c.include_input && c.n_coarse % 32 == 0 && p.scene.Vc <= kMaxColorViews &&
+         c.include_input && (p.xyz != nullptr || c.n_coarse % 32 == 0) && p.scene.Vc <= kMaxColorViews &&
          pixels * (p.mlp.Hd / 4) < (int64_t)0x7fffffff;   // tap offsets are 32-bit (float4 units)
 }
 
-template <int HD, bool kExact>
+template <int HD, bool kExact, bool kPoints>
 static cudaError_t launch_tc_t(const KernelParams& p, cudaStream_t stream) {
   using Lt = tcr::L<HD>;
-  auto kern = tcr::render_tc_kernel<HD, kExact>;
+  auto kern = tcr::render_tc_kernel<HD, kExact, kPoints>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Lt::kSmemBytes);
   if (e != cudaSuccess) return e;
   // kCtasPerSm CTAs/SM by design (registers, shared memory, TMEM columns): ask for the full shared-memory carve-out,
@@ -438,17 +469,20 @@ static cudaError_t launch_tc_t(const KernelParams& p, cudaStream_t stream) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t n_pass = (p.n_items + 3) / 4;
+  const int64_t n_pass = kPoints ? (p.n_items + 127) / 128 : (p.n_items + 3) / 4;
   const int64_t cap = (int64_t)sms * Lt::kCtasPerSm;      // persistent: every CTA resident, strided over passes
   const int grid = (int)(n_pass < cap ? n_pass : cap);
   kern<<<grid, tcr::kThreads, Lt::kSmemBytes, stream>>>(p);
   return cudaGetLastError();
 }
 
-cudaError_t launch_tc(const KernelParams& p, cudaStream_t stream) {
+cudaError_t launch_tc(const KernelParams& p, bool points, cudaStream_t stream) {
   const bool exact = p.cfg.precision == 0;
-  if (p.mlp.Hd == 64) return exact ? launch_tc_t<64, true>(p, stream) : launch_tc_t<64, false>(p, stream);
-  return exact ? launch_tc_t<128, true>(p, stream) : launch_tc_t<128, false>(p, stream);
+  if (points) {   // query: exact tier only (it feeds occupancy thresholds / BEV profiles)
+    return p.mlp.Hd == 64 ? launch_tc_t<64, true, true>(p, stream) : launch_tc_t<128, true, true>(p, stream);
+  }
+  if (p.mlp.Hd == 64) return exact ? launch_tc_t<64, true, false>(p, stream) : launch_tc_t<64, false, false>(p, stream);
+  return exact ? launch_tc_t<128, true, false>(p, stream) : launch_tc_t<128, false, false>(p, stream);
 }
 
 int tc_barrier_timeouts() {
