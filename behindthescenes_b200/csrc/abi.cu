@@ -16,6 +16,7 @@ size_t bwd_smem_bytes(int Hd, int p_pad, int K, int n_blocks);
 bool tc_supported(const KernelParams& p);
 cudaError_t launch_tc(const KernelParams& p, bool points, cudaStream_t stream);
 int tc_barrier_timeouts();
+int fold_barrier_timeouts();
 cudaError_t launch_pack_images(const float* img, int nv_total, int Cc, int Hc, int Wc, float* out, cudaStream_t stream);
 }  // namespace bts
 
@@ -59,7 +60,7 @@ extern "C" {
 int bts_abi_version(void) { return BTS_ABI_VERSION; }
 const char* bts_last_error(void) { return g_err; }
 const char* bts_last_kernel(void) { return g_kernel; }
-int bts_debug_tc_timeouts(void) { return bts::tc_barrier_timeouts(); }
+int bts_debug_tc_timeouts(void) { return bts::tc_barrier_timeouts() + bts::fold_barrier_timeouts(); }
 
 int bts_fold_features(const float* feat_nchw, int32_t n, int32_t C, int32_t H, int32_t W, const float* w_in,
                       int32_t ld_w_in, const float* b_in, int32_t Hd, const float* empty_feature_or_null, float* G_out,

@@ -6,6 +6,8 @@
 //   pack_images   : colour views NCHW -> channels-last padded to 4 (one 16-byte load per bilinear tap).
 // Reference tensors: grid_f_features / grid_c_imgs as cached by BTSNet.encode (models/bts/model/models_bts.py:126-136);
 // weight = mlp_coarse.lin_in.weight[:, :C] (models/common/model/resnetfc.py:88, input order models_bts.py:184).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace bts {
@@ -89,9 +91,25 @@ __global__ void pack_images_kernel(const float* __restrict__ img, int Cc, int64_
   out[i] = o;
 }
 
+bool fold_tc_supported(const float* feat, int C, int64_t HW, int Hd);
+cudaError_t launch_fold_tc(const float* feat, int n, int C, int64_t HW, const float* w_in, int ld, const float* b_in, int Hd,
+                           float* G, cudaStream_t stream);
+
 cudaError_t launch_fold(const float* feat, int n, int C, int H, int W, const float* w_in, int ld, const float* b_in, int Hd,
                         const float* empty, float* G, float* g_empty, cudaStream_t stream) {
   const int64_t HW = (int64_t)H * W;
+  // tensor-core path (TMA-fed tcgen05 GEMM, fold_tc.cu) whenever the frame qualifies; BTS_FOLD_SIMT=1 forces the
+  // CUDA-core kernel (tests compare the two)
+  const char* force_simt = getenv("BTS_FOLD_SIMT");
+  if (!(force_simt && force_simt[0] == '1') && fold_tc_supported(feat, C, HW, Hd)) {
+    cudaError_t e = launch_fold_tc(feat, n, C, HW, w_in, ld, b_in, Hd, G, stream);
+    if (e != cudaSuccess) return e;
+    if (empty && g_empty) {
+      fold_empty_kernel<<<(Hd + 127) / 128, 128, 0, stream>>>(empty, C, w_in, ld, Hd, b_in, g_empty);
+      e = cudaGetLastError();
+    }
+    return e;
+  }
   dim3 grid((unsigned)((HW + kFoldPix - 1) / kFoldPix), (unsigned)n);
   switch (Hd / 8) {
     case 4: fold_features_kernel<4><<<grid, 256, 0, stream>>>(feat, C, HW, w_in, ld, b_in, G); break;

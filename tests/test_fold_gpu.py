@@ -1,0 +1,67 @@
+"""GPU: bts_fold_features (called through the raw C ABI with device pointers) -- TMA-fed tcgen05 path vs the CUDA-core
+kernel vs an fp64 reference of G = W_in[:, :C] F + b_in."""
+import os
+
+import pytest
+import torch
+
+from behindthescenes_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _fold(feat, w_in, b_in, Hd, empty=None, force_simt=False):
+    lib = _lib.load()
+    n, C, H, W = feat.shape
+    G = torch.empty((n, H, W, Hd), device="cuda")
+    ge = torch.empty((Hd,), device="cuda") if empty is not None else None
+    old = os.environ.get("BTS_FOLD_SIMT")
+    os.environ["BTS_FOLD_SIMT"] = "1" if force_simt else "0"
+    try:
+        rc = lib.bts_fold_features(feat.data_ptr(), n, C, H, W, w_in.data_ptr(), w_in.shape[1], b_in.data_ptr(), Hd,
+                                   None if empty is None else empty.data_ptr(), G.data_ptr(),
+                                   None if ge is None else ge.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    finally:
+        if old is None:
+            os.environ.pop("BTS_FOLD_SIMT", None)
+        else:
+            os.environ["BTS_FOLD_SIMT"] = old
+    _lib.check(rc, "bts_fold_features")
+    torch.cuda.synchronize()
+    return G, ge
+
+
+@pytest.mark.parametrize("n,C,Hd,H,W", [(2, 64, 64, 192, 640), (1, 32, 32, 24, 36), (3, 64, 128, 13, 20), (1, 64, 32, 7, 12),
+                                        (1, 64, 64, 13, 21), (1, 48, 64, 16, 16)])
+def test_fold_matches_fp64_and_both_kernels_agree(n, C, Hd, H, W):
+    g = torch.Generator().manual_seed(n * 1000 + C + Hd + H)
+    feat = (torch.randn((n, C, H, W), generator=g) * 3).cuda()
+    w_in = torch.randn((Hd, C + 39), generator=g).cuda()
+    b_in = torch.randn((Hd,), generator=g).cuda()
+    empty = torch.randn((C,), generator=g).cuda()
+    ref = torch.einsum("kc,nchw->nhwk", w_in[:, :C].double(), feat.double()) + b_in.double()
+    scale = ref.abs().max().item()
+    G_tc, ge_tc = _fold(feat, w_in, b_in, Hd, empty)                  # tensor-core path where the frame qualifies
+    G_si, ge_si = _fold(feat, w_in, b_in, Hd, empty, force_simt=True)
+    assert _lib.load().bts_debug_tc_timeouts() == 0
+    for G in (G_tc, G_si):
+        assert torch.isfinite(G).all()
+        assert (G.double() - ref).abs().max().item() <= 3e-6 * scale
+    assert (G_tc - G_si).abs().max().item() <= 3e-6 * scale
+    ge_ref = w_in[:, :C].double() @ empty.double() + b_in.double()
+    assert (ge_tc.double() - ge_ref).abs().max().item() <= 1e-5 and torch.equal(ge_tc, ge_si)
+
+
+def test_fold_of_values_that_stress_the_tf32_split():
+    """Large dynamic range, exact powers of two and values whose low mantissa bits are all set."""
+    C, Hd, H, W = 64, 64, 8, 16
+    feat = torch.zeros((1, C, H, W))
+    feat[0, :, 0, :] = torch.tensor([1.0 + 2.0 ** -23, 65504.0, 1e-20, -3.999999, 0.1, 1e6, -1e-6, 7.0]).repeat(2)[:W].view(1, W)
+    feat[0, :, 1:, :] = torch.randn((C, H - 1, W)) * torch.logspace(-6, 6, C).view(C, 1, 1)
+    w_in = torch.randn((Hd, C + 39))
+    b_in = torch.zeros(Hd)
+    ref = torch.einsum("kc,nchw->nhwk", w_in[:, :C].double(), feat.double())
+    G, _ = _fold(feat.cuda(), w_in.cuda(), b_in.cuda(), Hd)
+    err = (G.double().cpu() - ref).abs()
+    bound = 4e-6 * torch.einsum("kc,nchw->nhwk", w_in[:, :C].abs().double(), feat.abs().double()) + 1e-30
+    assert (err <= bound).all()
