@@ -1,7 +1,7 @@
 """Training-shaped step (BASELINE config 3 flavour): forward + backward of the render path on patch rays.
 Ours (fused fwd + bts_render_bwd) vs the reference op chain with torch autograd on the same GPU.  Run under gpurun."""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from behindthescenes_b200 import synthetic as syn
 from tests import grad_util as gu
