@@ -118,3 +118,36 @@ def test_encode_caches_like_the_reference():
     assert torch.allclose(net.grid_c_poses_w2c, torch.inverse(wl.poses_c2w)[:, wl.ids_render])
     with pytest.raises(NotImplementedError):
         net.encode(wl.images, wl.Ks, wl.poses_c2w, combine_ids=[(0, 1)])
+
+
+@needs_ref
+def test_reference_consumers_accept_the_output_contract():
+    """The dict the drop-in returns must be consumable by the reference's own downstream code: ImageRaySampler.reconstruct
+    (models/bts/model/ray_sampler.py:262-321) and distance_to_z (utils/projection_operations.py:4-16), exactly as
+    models/bts/evaluator.py:68-79 chains them.  The oracle produces tensors with the drop-in's shapes/keys on the CPU
+    (the GPU parity tests check that the CUDA path returns the same dict)."""
+    import importlib
+    from oracle import bts_oracle as orc
+    from tests.golden_io import mlp_params
+    ref = ref_import.load_reference()
+    proj_ops = importlib.import_module("utils.projection_operations")
+    H, W = 12, 20
+    wl = syn.cfg2_kitti360_eval(H=H, W=W, K=32, stereo=True)
+    net, wrapped = _ours(wl)
+    sd = {k: v for k, v in net.state_dict().items() if not k.startswith("encoder.")}
+    st = orc.encode_state(wl.images, wl.Ks, wl.poses_c2w, wl.feats, wl.ids_encoder, wl.ids_render)
+    out = orc.render(st, mlp_params(sd), orc.FieldConfig.from_model_conf(wl.model_conf),
+                     orc.RenderConfig.from_renderer_conf(wl.renderer_conf), wl.rays, u=wl.u,
+                     empty_feature=sd.get("empty_feature"), want_weights=True, want_alphas=True)
+    render_dict = dict(out)
+    render_dict["fine"] = dict(render_dict["coarse"])                 # evaluator.py:70-71
+    sampler = ref.ImageRaySampler(3.0, 80.0)
+    rays_ref, _ = sampler.sample(wl.images * 0.5 + 0.5, wl.poses_c2w, wl.Ks)
+    assert torch.allclose(rays_ref, wl.rays, atol=1e-6)               # our synthetic.gen_rays == the reference's sampler
+    render_dict["rgb_gt"] = torch.zeros((1, 2 * H * W, 3))
+    render_dict = sampler.reconstruct(render_dict)
+    c = render_dict["coarse"]
+    assert c["depth"].shape == (1, 2, H, W) and c["rgb"].shape == (1, 2, H, W, 1, 3)
+    assert c["weights"].shape == (1, 2, H, W, 32) and c["invalid"].shape == (1, 2, H, W, 32, 1)
+    z = proj_ops.distance_to_z(c["depth"], wl.Ks)
+    assert z.shape == (1, 2, H, W) and torch.isfinite(z).all()
