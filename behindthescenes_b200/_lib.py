@@ -10,7 +10,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libbts_b200.so")
 
 BTS_MAX_BLOCKS = 8
-ABI_VERSION = 5
+ABI_VERSION = 6
 _fp = C.POINTER(C.c_float)
 
 
@@ -41,7 +41,7 @@ class BtsRenderCfg(C.Structure):
 class BtsRenderOut(C.Structure):
     _fields_ = [("rgb", C.c_void_p), ("depth", C.c_void_p), ("invalid", C.c_void_p), ("weights", C.c_void_p),
                 ("alphas", C.c_void_p), ("z_samps", C.c_void_p), ("rgb_samps", C.c_void_p),
-                ("invalid_mass", C.c_void_p), ("depth_z", C.c_void_p)]
+                ("invalid_mass", C.c_void_p), ("sigma", C.c_void_p), ("depth_z", C.c_void_p)]
 
 
 class BtsRayGen(C.Structure):
@@ -72,7 +72,7 @@ EXPORTS = {
     "bts_render_views_fwd": (C.c_int, [C.POINTER(BtsScene), C.POINTER(BtsMlp), C.POINTER(BtsRenderCfg), C.POINTER(BtsRayGen),
                                        C.c_int64, C.c_void_p, C.c_uint64, C.POINTER(BtsRenderOut), C.c_void_p]),
     "bts_render_bwd": (C.c_int, [C.POINTER(BtsScene), C.POINTER(BtsMlp), C.POINTER(BtsRenderCfg), C.c_void_p,
-                                 C.c_int64, C.c_int64, C.c_void_p, C.c_uint64, C.POINTER(BtsRenderGrad),
+                                 C.c_int64, C.c_int64, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(BtsRenderGrad),
                                  C.POINTER(BtsParamGrad), C.c_void_p]),
     "bts_query_field": (C.c_int, [C.POINTER(BtsScene), C.POINTER(BtsMlp), C.POINTER(BtsRenderCfg), C.c_void_p,
                                   C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

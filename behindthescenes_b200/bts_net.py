@@ -285,7 +285,8 @@ class BTSNet(nn.Module):
         return self._render_rays_raw(renderer, rays, u, seed, **wants, **extras)
 
     def _render_rays_raw(self, renderer, rays, u=None, seed=0, want_weights=False, want_alphas=False, want_z_samps=False,
-                         want_rgb_samps=False, want_invalid=True, want_invalid_mass=False, want_depth_z=False, gen=None):
+                         want_rgb_samps=False, want_invalid=True, want_invalid_mass=False, want_depth_z=False, gen=None,
+                         want_sigma=False):
         """``rays`` (n,R,8), or ``rays=None`` with ``gen = (poses_c2w (n,v,4,4), Ks (n,v,3,3), H, W, z_near, z_far,
         norm_dir)`` to generate one ray per pixel of every view inside the kernel (bts_render_views_fwd)."""
         lib = _lib.load()
@@ -318,6 +319,8 @@ class BTSNet(nn.Module):
             ret["invalid_mass"] = new(n, R, Vc)
         if want_depth_z:
             ret["depth_z"] = new(n, R)
+        if want_sigma:
+            ret["sigma"] = new(n, R, K)
         if want_weights:
             ret["weights"] = new(n, R, K)
         if want_alphas:
@@ -353,8 +356,9 @@ class _RenderFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, renderer, rays, u, seed, wants, keys, feats, w_in, b_in, w_out, b_out, empty, fc0_w, fc0_b, fc1_w, fc1_b):
         with torch.no_grad():
-            out = net._render_rays_raw(renderer, rays, u=u, seed=seed, **wants)
+            out = net._render_rays_raw(renderer, rays, u=u, seed=seed, want_sigma=True, **wants)
         ctx.net, ctx.renderer, ctx.seed, ctx.keys = net, renderer, seed, keys
+        ctx.sigma = out.pop("sigma")
         ctx.has_u = u is not None
         ctx.has_block = fc0_w.numel() > 0
         ctx.K = int(renderer.n_coarse)
@@ -402,8 +406,8 @@ class _RenderFunction(torch.autograd.Function):
         u_d = _dev_f32(u.to(dev)) if ctx.has_u else None
         stream = torch.cuda.current_stream(dev).cuda_stream
         rc = lib.bts_render_bwd(C.byref(scene), C.byref(mlp), C.byref(cfg), rays_d.data_ptr(), n, R,
-                                None if u_d is None else u_d.data_ptr(), int(ctx.seed) & (2 ** 64 - 1), C.byref(up),
-                                C.byref(pg), stream)
+                                None if u_d is None else u_d.data_ptr(), int(ctx.seed) & (2 ** 64 - 1),
+                                ctx.sigma.data_ptr(), C.byref(up), C.byref(pg), stream)
         _lib.check(rc, "bts_render_bwd")
         # dense tail of the fold G = F W_F^T + b_in (two plain GEMMs)
         nb, _, _, H, W = feats.shape

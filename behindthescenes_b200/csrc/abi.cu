@@ -130,8 +130,8 @@ int bts_render_views_fwd(const BtsScene* scene, const BtsMlp* mlp, const BtsRend
 }
 
 int bts_render_bwd(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg* cfg, const float* rays, int64_t n,
-                   int64_t R, const float* u_or_null, uint64_t seed, const BtsRenderGrad* upstream,
-                   const BtsParamGrad* grads, bts_stream_t stream) {
+                   int64_t R, const float* u_or_null, uint64_t seed, const float* saved_sigma_or_null,
+                   const BtsRenderGrad* upstream, const BtsParamGrad* grads, bts_stream_t stream) {
   int rc = check_common(scene, mlp, cfg);
   if (rc != BTS_OK) return rc;
   if (!rays || !upstream || !grads) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_render_bwd: rays/upstream/grads is null");
@@ -152,6 +152,7 @@ int bts_render_bwd(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg*
   bp.k.scene = *scene; bp.k.mlp = *mlp; bp.k.cfg = *cfg;
   bp.k.rays = rays; bp.k.u = u_or_null; bp.k.n_items = n * R; bp.k.per_batch = R; bp.k.seed = seed;
   bp.k.p_pad = (mlp->P + 3) & ~3;
+  bp.saved_sigma = saved_sigma_or_null;
   bp.g_rgb = upstream->rgb; bp.g_depth = upstream->depth; bp.g_weights = upstream->weights; bp.g_alphas = upstream->alphas;
   bp.d_G = grads->d_G; bp.d_g_empty = grads->d_g_empty; bp.d_w_pe = grads->d_w_pe; bp.d_w_out = grads->d_w_out;
   bp.d_b_out = grads->d_b_out;

@@ -10,6 +10,7 @@ struct BwdParams {
   const float* g_depth;    // (n*R)
   const float* g_weights;  // (n*R, K)
   const float* g_alphas;   // (n*R, K)
+  const float* saved_sigma;  // (n*R, K) from the forward, or null -> sweep 1 re-evaluates the MLP
   // accumulated outputs (caller zero-initialises)
   float* d_G;              // (n, H, W, Hd)
   float* d_g_empty;        // (Hd)

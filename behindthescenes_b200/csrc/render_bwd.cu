@@ -120,77 +120,79 @@ __global__ void __launch_bounds__(kBwdWarps * 32, kBlock ? 2 : 3) render_bwd_ker
       const float z_first_of_next = __shfl_sync(0xffffffffu, z_ahead, 0);
       if (lane == 31) z_next = z_first_of_next;
       const float X = __fadd_rn(ro0, __fmul_rn(z, rd0)), Y = __fadd_rn(ro1, __fmul_rn(z, rd1)), Z = __fadd_rn(ro2, __fmul_rn(z, rd2));
-      const Proj pf = project(vf, X, Y, Z);
-      {
-        positional_code(cfg, pf.u, pf.v, depth_code(cfg, pf), w_pe + lane, 32);
-        for (int j = P; j < Ppad; ++j) w_pe[j * 32 + lane] = 0.0f;
-        const Taps t = bilinear_taps(pf.u, pf.v, H, W);
-        float4 a, w;
-        a.x = __int_as_float((int)((b * H + t.y0) * (int64_t)W + t.x0));
-        a.y = __int_as_float(t.dx);
-        a.z = __int_as_float(t.dy * W);
-        a.w = __int_as_float((valid ? 1 : 0) | ((use_empty && pf.invalid) ? 2 : 0));
-        w.x = t.wx0; w.y = t.wx1; w.z = t.wy0; w.w = t.wy1;
-        reinterpret_cast<float4*>(w_taps)[lane * 2 + 0] = a;
-        reinterpret_cast<float4*>(w_taps)[lane * 2 + 1] = w;
-      }
-      __syncwarp();
       float logit = 0.0f;
-      const int n_valid = min(32, K - c0);
-      for (int s0 = 0; s0 < n_valid; s0 += 8) {
-        float acc[8][NU];
-#pragma unroll
-        for (int ss = 0; ss < 8; ++ss) {
-          const float4 a = reinterpret_cast<const float4*>(w_taps)[(s0 + ss) * 2 + 0];
-          const float4 w = reinterpret_cast<const float4*>(w_taps)[(s0 + ss) * 2 + 1];
-          const int flags = __float_as_int(a.w);
-#pragma unroll
-          for (int n = 0; n < NU; ++n) {
-            float g = 0.0f;
-            if (flags & 2) g = __ldg(p.scene.g_empty + lane * NU + n);
-            else if (flags & 1) {
-              const float* g00 = p.scene.G + (size_t)__float_as_int(a.x) * Hd + lane * NU + n;
-              const float* g10 = g00 + (size_t)__float_as_int(a.z) * Hd;
-              const size_t dxo = (size_t)__float_as_int(a.y) * Hd;
-              g = fmaf(__ldg(g10 + dxo), w.y * w.w, fmaf(__ldg(g10), w.x * w.w, fmaf(__ldg(g00 + dxo), w.y * w.z, __ldg(g00) * (w.x * w.z))));
-            }
-            acc[ss][n] = g;
-          }
+      if (bp.saved_sigma == nullptr) {
+      const Proj pf = project(vf, X, Y, Z);
+        {
+          positional_code(cfg, pf.u, pf.v, depth_code(cfg, pf), w_pe + lane, 32);
+          for (int j = P; j < Ppad; ++j) w_pe[j * 32 + lane] = 0.0f;
+          const Taps t = bilinear_taps(pf.u, pf.v, H, W);
+          float4 a, w;
+          a.x = __int_as_float((int)((b * H + t.y0) * (int64_t)W + t.x0));
+          a.y = __int_as_float(t.dx);
+          a.z = __int_as_float(t.dy * W);
+          a.w = __int_as_float((valid ? 1 : 0) | ((use_empty && pf.invalid) ? 2 : 0));
+          w.x = t.wx0; w.y = t.wx1; w.z = t.wy0; w.w = t.wy1;
+          reinterpret_cast<float4*>(w_taps)[lane * 2 + 0] = a;
+          reinterpret_cast<float4*>(w_taps)[lane * 2 + 1] = w;
         }
-        for (int j = 0; j < P; ++j) {
-          float wv[NU];
-#pragma unroll
-          for (int n = 0; n < NU; ++n) wv[n] = s_wpe[j * Hd + lane * NU + n];
-          const float4 c0v = *reinterpret_cast<const float4*>(w_pe + j * 32 + s0);
-          const float4 c1v = *reinterpret_cast<const float4*>(w_pe + j * 32 + s0 + 4);
-          const float cv[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
-#pragma unroll
-          for (int ss = 0; ss < 8; ++ss)
-#pragma unroll
-            for (int n = 0; n < NU; ++n) acc[ss][n] = fmaf(wv[n], cv[ss], acc[ss][n]);
-        }
-        if constexpr (kBlock) {
+        __syncwarp();
+        const int n_valid = min(32, K - c0);
+        for (int s0 = 0; s0 < n_valid; s0 += 8) {
+          float acc[8][NU];
 #pragma unroll
           for (int ss = 0; ss < 8; ++ss) {
-            const float a0 = fmaxf(acc[ss][0], 0.0f);
-            float t = s_b0[lane];
-            for (int i = 0; i < 32; ++i) t = fmaf(s_w0t[i * 32 + lane], __shfl_sync(0xffffffffu, a0, i), t);
-            const float a1 = fmaxf(t, 0.0f);
-            float d = s_b1[lane];
-            for (int i = 0; i < 32; ++i) d = fmaf(s_w1t[i * 32 + lane], __shfl_sync(0xffffffffu, a1, i), d);
-            acc[ss][0] += d;
+            const float4 a = reinterpret_cast<const float4*>(w_taps)[(s0 + ss) * 2 + 0];
+            const float4 w = reinterpret_cast<const float4*>(w_taps)[(s0 + ss) * 2 + 1];
+            const int flags = __float_as_int(a.w);
+#pragma unroll
+            for (int n = 0; n < NU; ++n) {
+              float g = 0.0f;
+              if (flags & 2) g = __ldg(p.scene.g_empty + lane * NU + n);
+              else if (flags & 1) {
+                const float* g00 = p.scene.G + (size_t)__float_as_int(a.x) * Hd + lane * NU + n;
+                const float* g10 = g00 + (size_t)__float_as_int(a.z) * Hd;
+                const size_t dxo = (size_t)__float_as_int(a.y) * Hd;
+                g = fmaf(__ldg(g10 + dxo), w.y * w.w, fmaf(__ldg(g10), w.x * w.w, fmaf(__ldg(g00 + dxo), w.y * w.z, __ldg(g00) * (w.x * w.z))));
+              }
+              acc[ss][n] = g;
+            }
+          }
+          for (int j = 0; j < P; ++j) {
+            float wv[NU];
+#pragma unroll
+            for (int n = 0; n < NU; ++n) wv[n] = s_wpe[j * Hd + lane * NU + n];
+            const float4 c0v = *reinterpret_cast<const float4*>(w_pe + j * 32 + s0);
+            const float4 c1v = *reinterpret_cast<const float4*>(w_pe + j * 32 + s0 + 4);
+            const float cv[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+#pragma unroll
+            for (int ss = 0; ss < 8; ++ss)
+#pragma unroll
+              for (int n = 0; n < NU; ++n) acc[ss][n] = fmaf(wv[n], cv[ss], acc[ss][n]);
+          }
+          if constexpr (kBlock) {
+#pragma unroll
+            for (int ss = 0; ss < 8; ++ss) {
+              const float a0 = fmaxf(acc[ss][0], 0.0f);
+              float t = s_b0[lane];
+              for (int i = 0; i < 32; ++i) t = fmaf(s_w0t[i * 32 + lane], __shfl_sync(0xffffffffu, a0, i), t);
+              const float a1 = fmaxf(t, 0.0f);
+              float d = s_b1[lane];
+              for (int i = 0; i < 32; ++i) d = fmaf(s_w1t[i * 32 + lane], __shfl_sync(0xffffffffu, a1, i), d);
+              acc[ss][0] += d;
+            }
+          }
+#pragma unroll
+          for (int ss = 0; ss < 8; ++ss) {
+            float part = 0.0f;
+#pragma unroll
+            for (int n = 0; n < NU; ++n) part = fmaf(fmaxf(acc[ss][n], 0.0f), s_wout[lane * NU + n], part);
+            const float tot = warp_sum(part);
+            if (lane == s0 + ss) logit = tot + b_out;
           }
         }
-#pragma unroll
-        for (int ss = 0; ss < 8; ++ss) {
-          float part = 0.0f;
-#pragma unroll
-          for (int n = 0; n < NU; ++n) part = fmaf(fmaxf(acc[ss][n], 0.0f), s_wout[lane * NU + n], part);
-          const float tot = warp_sum(part);
-          if (lane == s0 + ss) logit = tot + b_out;
-        }
       }
-      const float sigma = softplus(logit);
+      const float sigma = bp.saved_sigma ? (valid ? __ldg(bp.saved_sigma + ray * K + k) : 0.0f) : softplus(logit);
       __syncwarp();
       // compositing forward (nerf.py:283-294)
       const float delta = (k + 1 < K) ? __fsub_rn(z_next, z) : 1e10f;

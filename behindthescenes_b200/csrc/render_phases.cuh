@@ -31,6 +31,7 @@ __device__ __forceinline__ float composite_chunk(const KernelParams& p, int lane
     if (p.out.weights) p.out.weights[sample_id] = wgt;
     if (p.out.alphas) p.out.alphas[sample_id] = alpha;
     if (p.out.z_samps) p.out.z_samps[sample_id] = z;
+    if (p.out.sigma) p.out.sigma[sample_id] = sigma;
   }
   return wgt;
 }

@@ -347,16 +347,66 @@ def run_ours(args):
                 e2e_ev[i][1].record()
             torch.cuda.synchronize(dev)
         sync_all()
-    e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_ev) / args.steps
-    clocks = sampler.stop() if sampler else None                     # covers warm-up, timed loop, kernel loop, e2e loop
+    e2e_seq_ms = sum(a.elapsed_time(b) for a, b in e2e_ev) / args.steps
+
+    # The same steps as a 3-stage stream pipeline (how a serving loop runs them): H2D of frame i+1 and D2H of frame i-1
+    # overlap the render of frame i on separate streams; every step still moves its own inputs and its own result.
+    # No L2 flush here: the per-step inputs rotate over 5 feature maps (5 x 31.5 MB > L2) and arrive by DMA.
+    feats_rot = [torch.randn_like(net.grid_f_features[0]) for _ in range(5)]
+    s_in, s_c, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    slots = 3
+    img_d = [torch.empty_like(img_dev) for _ in range(slots)]
+    pos_d = [torch.empty_like(poses_dev) for _ in range(slots)]
+    Ks_d = [torch.empty_like(Ks_dev) for _ in range(slots)]
+    dep_h = [torch.empty_like(depth_host).pin_memory() for _ in range(slots)]
+    rgb_h = [torch.empty_like(rgb_host).pin_memory() for _ in range(slots)]
+    keep, ev_in, ev_c, ev_out = {}, {}, {}, {}
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_pipe = args.steps + 6
+    torch.cuda.synchronize(dev)
+    with torch.no_grad():
+        for i in range(n_pipe):
+            j = i % slots
+            with torch.cuda.stream(s_in):
+                if i - slots in ev_out:
+                    s_in.wait_event(ev_c[i - slots])                 # slot j's device inputs were consumed
+                if i == 3:
+                    t0.record(s_in)                                  # steps 0-2 fill the pipeline (untimed)
+                img_d[j].copy_(img_host, non_blocking=True)
+                pos_d[j].copy_(poses_host, non_blocking=True)
+                Ks_d[j].copy_(Ks_host, non_blocking=True)
+                ev_in[i] = torch.cuda.Event(); ev_in[i].record(s_in)
+            with torch.cuda.stream(s_c):
+                s_c.wait_event(ev_in[i])
+                net.grid_f_features = [feats_rot[i % len(feats_rot)]]
+                net.grid_c_imgs = (img_d[j] * 0.5 + 0.5)[:, wl.ids_render]
+                net.invalidate_scene()
+                o = wrapped.render_views(pos_d[j], Ks_d[j], H_img, W_img, wl.model_conf["z_near"], wl.model_conf["z_far"],
+                                         want_depth_z=True, **wants)["coarse"]
+                ev_c[i] = torch.cuda.Event(); ev_c[i].record(s_c)
+            keep[i] = o                                              # outputs stay alive until their D2H has been issued+done
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_c[i])
+                if i - slots in ev_out:
+                    ev_out[i - slots].synchronize()                  # host buffer j is free again (its consumer would read it here)
+                dep_h[j].copy_(o["depth_z"], non_blocking=True)
+                rgb_h[j].copy_(o["rgb"], non_blocking=True)
+                ev_out[i] = torch.cuda.Event(); ev_out[i].record(s_out)
+                if i == n_pipe - 4:
+                    t1.record(s_out)                                 # end of the last timed step (args.steps steps after t0)
+            keep.pop(i - slots, None)
+        torch.cuda.synchronize(dev)
+        sync_all()
+    e2e_ms = t0.elapsed_time(t1) / args.steps
+    clocks = sampler.stop() if sampler else None                     # covers warm-up, timed loop, kernel loop, e2e loops
     gc.enable()
     h2d_bytes = int((img_host.numel() + poses_host.numel() + Ks_host.numel()) * 4)
 
     # ---- max over ranks ----------------------------------------------------------------------------------------------
-    t = torch.tensor([step_ms, e2e_ms, kern_ms, prep_ms], device=dev, dtype=torch.float64)
+    t = torch.tensor([step_ms, e2e_ms, kern_ms, prep_ms, e2e_seq_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    step_ms, e2e_ms, kern_ms_max, prep_ms = (float(x) for x in t.tolist())
+    step_ms, e2e_ms, kern_ms_max, prep_ms, e2e_seq_ms = (float(x) for x in t.tolist())
     total_rays = n_frame * world
     value = total_rays / (step_ms * 1e-3)
     e2e_value = total_rays / (e2e_ms * 1e-3)
@@ -387,7 +437,9 @@ def run_ours(args):
                            "l2": "256 MiB flush before every timed step", "precision_tier": "exact-fp32" if args.precision == 0 else "fast",
                            "kernel": kernel_name, "ms_fold_pack": prep_ms, "ms_render": render_ms, "ms_metric_allreduce": metric_ms, "diag": diag},
                 "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes,
-                        "d2h_bytes_per_step": int(depth_host.numel() * 4 + rgb_host.numel() * 4), "ms_per_step": e2e_ms},
+                        "d2h_bytes_per_step": int(depth_host.numel() * 4 + rgb_host.numel() * 4), "ms_per_step": e2e_ms,
+                        "how": "3-stream pipeline (H2D | fold+pack+render | D2H), every step copies its own inputs and result",
+                        "ms_per_step_unpipelined": e2e_seq_ms},
                 "gpu_launches": args.steps * (3 + 1),          # fold, fold_empty, pack_images, render per step (ours)
                 "roofline": roof, "clocks": clocks, "wall_s_timed_loop": wall,
                 "depth_sum_check": float(metric["depth_sum"].item())}

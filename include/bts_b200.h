@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BTS_ABI_VERSION 5
+#define BTS_ABI_VERSION 6
 #define BTS_MAX_BLOCKS 8   /* ResnetFC blocks supported by the kernels */
 
 typedef struct CUstream_st* bts_stream_t; /* == cudaStream_t */
@@ -110,6 +110,8 @@ typedef struct {
   /* fused consumers of the per-sample outputs, all optional:                                  */
   float* invalid_mass; /* (n, R, Vc)  sum_k invalid[k,v] * weights[k]  -- the "weight guided" invalid test of
                           models/bts/model/loss.py:105-108 and scripts/inference_setup.py:192 without the (R,K,Vc) tensor */
+  float* sigma;        /* (n, R, K)   per-sample density (softplus output, models_bts.py:313): saved by the autograd
+                          node so that bts_render_bwd does not have to re-evaluate the MLP for the compositing pass  */
   float* depth_z;      /* (n, R)      z-depth = depth * (unit-ray z in its camera), utils/projection_operations.py:4-16;
                           only with in-kernel ray generation (BtsRayGen)                                            */
 } BtsRenderOut;
@@ -175,13 +177,13 @@ typedef struct {
 
 /* Backward of bts_render_fwd (what torch autograd does for the reference's op chain during
  * `loss.backward()`, utils/base_trainer.py:297): recomputes the forward per ray from the same inputs (same `u` or
- * `seed`), then back-propagates through compositing (nerf.py:283-304), softplus, lin_out and lin_in.  The dense tail
+ * `seed`; with `saved_sigma` (n,R,K) from the forward's BtsRenderOut.sigma the MLP is evaluated once instead of twice), then back-propagates through compositing (nerf.py:283-304), softplus, lin_out and lin_in.  The dense tail
  * of the chain is the caller's: dF = d_G * W_in[:, :C], dW_in[:, :C] = d_G^T * F (+ d_g_empty x empty_feature),
  * db_in = sum(d_G) + d_g_empty.  Supports n_blocks = 0 with d_hidden <= 64 (the KITTI training configs) and
  * n_blocks = 1 with d_hidden = 32 (the RE10K training config). */
 int bts_render_bwd(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg* cfg, const float* rays, int64_t n,
-                   int64_t R, const float* u_or_null, uint64_t seed, const BtsRenderGrad* upstream,
-                   const BtsParamGrad* grads, bts_stream_t stream);
+                   int64_t R, const float* u_or_null, uint64_t seed, const float* saved_sigma_or_null,
+                   const BtsRenderGrad* upstream, const BtsParamGrad* grads, bts_stream_t stream);
 
 /* Replaces a direct BTSNet.forward(xyz, only_density=...) point query (models_bts.py:266-338; callers
  * scripts/inference_setup.py:214, models/bts/evaluator_lidar.py:305).  xyz (n, P, 3).

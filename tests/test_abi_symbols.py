@@ -35,7 +35,7 @@ def test_every_declared_symbol_is_exported(lib):
     for n in _declared_functions():
         assert hasattr(lib, n), f"{n} declared in include/bts_b200.h but not exported"
         assert n in _lib.EXPORTS, f"{n} has no ctypes prototype"
-    assert lib.bts_abi_version() == 5
+    assert lib.bts_abi_version() == 6
     assert lib.bts_last_error() is not None
 
 
@@ -44,7 +44,7 @@ def test_struct_mirrors_match_header_layout():
     # sizes under the LP64 C ABI: int32 fields, 8-byte pointers, natural alignment
     assert ctypes.sizeof(_lib.BtsScene) == 16 + 4 * 8 + 16 + 3 * 8 + 8   # + same_view_mask (padded)
     assert ctypes.sizeof(_lib.BtsMlp) == 16 + 2 * 8 + 4 * 8 * 8 + 2 * 8
-    assert ctypes.sizeof(_lib.BtsRenderOut) == 9 * 8
+    assert ctypes.sizeof(_lib.BtsRenderOut) == 10 * 8
     assert ctypes.sizeof(_lib.BtsRayGen) == 2 * 8 + 4 * 4 + 2 * 4
     assert ctypes.sizeof(_lib.BtsRenderCfg) == 9 * 4 + 6 * 4 + 4 + 8 + 8  # 9 ints, 6 floats, pad, ptr, step+precision
 
