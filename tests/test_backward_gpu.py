@@ -100,3 +100,35 @@ def test_backward_unsupported_configs_raise():
         wrapped(wl.rays.cuda())                                     # parameters require grad -> autograd path -> blocks
     with torch.no_grad():
         wrapped(wl.rays.cuda())                                     # inference is fine
+
+
+@pytest.mark.parametrize("variant", ["white_linear_nocap", "distance_code_K32", "general_forward_kernel"])
+def test_backward_option_coverage_vs_oracle_autograd(variant):
+    """Renderer / field options that change the backward formulas: white background (rgb depends on sum of weights),
+    no hard alpha cap (last sample carries gradient), linear depth sampling + linear depth code, distance code, K=32,
+    in-frustum exits (learn_empty rows), and the CUDA-core forward (precision=2) feeding the same backward."""
+    P = syn._pose
+    if variant == "white_linear_nocap":
+        mc = syn.kitti_model_conf(learn_empty=True, z_near=0.5, z_far=20.0, inv_z=False)
+        rc = syn.kitti_renderer_conf(64, lindisp=False, hard_alpha_cap=False, white_bkgd=True)
+        wl = syn.make_workload("bw_white", H=24, W=64, poses=[P(), P(tx=0.3, yaw_deg=8.0)], model_conf=mc, renderer_conf=rc,
+                               ids_encoder=[0], ids_render=[0, 1], ray_poses=[P(tx=0.4, tz=0.5, yaw_deg=25.0)],
+                               ray_subsample=700, seed=81, lin_out_bias=-2.0)
+        prec = 0
+    elif variant == "distance_code_K32":
+        mc = syn.kitti_model_conf(learn_empty=True, code_mode="distance")
+        rc = syn.kitti_renderer_conf(32)
+        wl = syn.make_workload("bw_dist", H=24, W=64, poses=[P(), P(tx=0.54)], model_conf=mc, renderer_conf=rc,
+                               ids_encoder=[0], ids_render=[1], ray_poses=[P(tx=0.2, tz=-0.5, yaw_deg=12.0)],
+                               ray_subsample=700, seed=82, lin_out_bias=-3.0)
+        prec = 0
+    else:
+        wl = syn.cfg2_kitti360_eval(H=24, W=64, K=64, stereo=True, learn_empty=True, lin_out_bias=-4.0, seed=83, ray_subsample=700)
+        prec = 2
+    cpu_net, _ = syn.build_model(wl, "cpu")
+    sd = {k: v.clone() for k, v in cpu_net.state_dict().items() if not k.startswith("encoder.")}
+    got, _ = cuda_gradients(wl, sd, precision=prec)
+    ref = gu.oracle_gradients(wl, sd)
+    errs = {k: gu.rel_err(got[k], ref[k]) for k in ref}
+    print(variant, errs)
+    assert max(errs.values()) <= GRAD_REL_TOL, errs
