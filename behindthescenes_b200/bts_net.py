@@ -257,7 +257,10 @@ class BTSNet(nn.Module):
         ``utils/base_trainer.py:297``)."""
         wants = dict(want_weights=want_weights, want_alphas=want_alphas, want_z_samps=want_z_samps,
                      want_rgb_samps=want_rgb_samps)
-        if torch.is_grad_enabled() and not extras:
+        # the consumer-side output diet (no per-sample flags, invalid mass per ray) is also available when training: both
+        # are non-differentiable in the reference too (loss.py:105-108 only thresholds them)
+        diet = {k: extras[k] for k in ("want_invalid", "want_invalid_mass") if k in extras}
+        if torch.is_grad_enabled() and len(diet) == len(extras):
             feats = self.grid_f_features[self._scale] if self.grid_f_features is not None else None
             m = self.mlp_coarse
             diff = [feats, m.lin_in.weight, m.lin_in.bias, m.lin_out.weight, m.lin_out.bias,
@@ -267,8 +270,11 @@ class BTSNet(nn.Module):
                 if not (m.n_blocks == 0 and m.d_hidden <= 64) and not (m.n_blocks == 1 and m.d_hidden == 32):
                     raise NotImplementedError("backward of the B200 render path implements n_blocks=0 (d_hidden<=64) and "
                                               "n_blocks=1 with d_hidden=32 (the shipped KITTI / RE10K training configs)")
-                keys = ["rgb", "depth", "invalid"] + [k for k, w in (("weights", want_weights), ("alphas", want_alphas),
-                                                                    ("z_samps", want_z_samps), ("rgb_samps", want_rgb_samps)) if w]
+                keys = ["rgb", "depth"] + [k for k, w in (("invalid", diet.get("want_invalid", True)),
+                                                          ("invalid_mass", diet.get("want_invalid_mass", False)),
+                                                          ("weights", want_weights), ("alphas", want_alphas),
+                                                          ("z_samps", want_z_samps), ("rgb_samps", want_rgb_samps)) if w]
+                wants = dict(wants, **diet)
                 ef = diff[5] if diff[5] is not None else torch.zeros(0, device=rays.device)
                 if m.n_blocks == 1:
                     b0 = m.blocks[0]
@@ -280,8 +286,8 @@ class BTSNet(nn.Module):
                                              diff[3], diff[4], ef, *blk_t)
                 return dict(zip(keys, outs))
         if extras and torch.is_grad_enabled() and any(p.requires_grad for p in self.mlp_coarse.parameters()):
-            raise NotImplementedError("the fused-consumer outputs / in-kernel ray generation are inference-only: "
-                                      "call them under torch.no_grad()")
+            raise NotImplementedError("in-kernel ray generation / depth_z are inference-only: call them under "
+                                      "torch.no_grad()")
         return self._render_rays_raw(renderer, rays, u, seed, **wants, **extras)
 
     def _render_rays_raw(self, renderer, rays, u=None, seed=0, want_weights=False, want_alphas=False, want_z_samps=False,
@@ -364,7 +370,7 @@ class _RenderFunction(torch.autograd.Function):
         ctx.K = int(renderer.n_coarse)
         ctx.save_for_backward(rays, u if u is not None else rays.new_zeros(0), feats, w_in, empty)
         res = tuple(out[k] for k in keys)
-        ctx.mark_non_differentiable(*[out[k] for k in keys if k in ("invalid", "z_samps", "rgb_samps")])
+        ctx.mark_non_differentiable(*[out[k] for k in keys if k in ("invalid", "invalid_mass", "z_samps", "rgb_samps")])
         return res
 
     @staticmethod
@@ -414,9 +420,26 @@ class _RenderFunction(torch.autograd.Function):
         dG2 = dG.view(nb, H * W, Hd)
         W_F = w_in.detach()[:, :Cf]
         f2 = feats.detach().reshape(nb, Cf, H * W)
-        d_feats = torch.einsum("npk,kc->ncp", dG2, W_F).reshape(feats.shape) if ctx.needs_input_grad[7] else None
-        d_WF = torch.einsum("npk,ncp->kc", dG2, f2)
-        d_b_in = dG2.sum((0, 1)) + dge
+        need_df = ctx.needs_input_grad[7]
+        feats_c = feats.detach()
+        w_c = w_in.detach()
+        d_feats = d_WF = None
+        if feats_c.dtype == torch.float32 and feats_c.is_contiguous() and w_c.dtype == torch.float32 and w_c.stride(1) == 1:
+            d_feats = torch.empty_like(feats_c) if need_df else None
+            d_WF = torch.zeros((Hd, Cf), device=dev, dtype=torch.float32)
+            d_b = torch.zeros((Hd,), device=dev, dtype=torch.float32)
+            rc = lib.bts_fold_features_bwd(dG.data_ptr(), feats_c.data_ptr(), nb, Cf, H, W, w_c.data_ptr(), w_c.stride(0), Hd,
+                                           d_feats.data_ptr() if need_df else None, d_WF.data_ptr(), d_b.data_ptr(), stream)
+            if rc == 0:
+                d_b_in = d_b + dge
+            elif rc == -2:          # shape outside the tensor-core fold backward: dense formulation below
+                d_feats = d_WF = None
+            else:
+                _lib.check(rc, "bts_fold_features_bwd")
+        if d_WF is None:
+            d_feats = torch.einsum("npk,kc->ncp", dG2, W_F).reshape(feats.shape) if need_df else None
+            d_WF = torch.einsum("npk,ncp->kc", dG2, f2)
+            d_b_in = dG2.sum((0, 1)) + dge
         d_empty = None
         if empty.numel() > 0:
             d_WF = d_WF + torch.outer(dge, empty.detach())

@@ -5,6 +5,7 @@
 
 #include "common.cuh"
 #include "bwd_params.cuh"
+#include "patch_loss.cuh"
 
 namespace bts {
 cudaError_t launch_general(const KernelParams& p, bool points, cudaStream_t stream);
@@ -17,6 +18,12 @@ bool tc_supported(const KernelParams& p);
 cudaError_t launch_tc(const KernelParams& p, bool points, cudaStream_t stream);
 int tc_barrier_timeouts();
 int fold_barrier_timeouts();
+int fold_bwd_barrier_timeouts();
+bool fold_bwd_tc_supported(const float* dG, const float* feat, const float* d_feat, int C, int64_t HW, int Hd);
+cudaError_t launch_fold_bwd_tc(const float* dG, const float* feat, int n, int C, int64_t HW, const float* w_in, int ld, int Hd,
+                               float* d_feat, float* d_wf, float* d_b, cudaStream_t stream);
+cudaError_t launch_patch_loss(const PatchLossParams& p, bool backward, cudaStream_t stream);
+bool patch_loss_supported(int h, int w, int nv, int c);
 cudaError_t launch_pack_images(const float* img, int nv_total, int Cc, int Hc, int Wc, float* out, cudaStream_t stream);
 }  // namespace bts
 
@@ -60,7 +67,7 @@ extern "C" {
 int bts_abi_version(void) { return BTS_ABI_VERSION; }
 const char* bts_last_error(void) { return g_err; }
 const char* bts_last_kernel(void) { return g_kernel; }
-int bts_debug_tc_timeouts(void) { return bts::tc_barrier_timeouts() + bts::fold_barrier_timeouts(); }
+int bts_debug_tc_timeouts(void) { return bts::tc_barrier_timeouts() + bts::fold_barrier_timeouts() + bts::fold_bwd_barrier_timeouts(); }
 
 int bts_fold_features(const float* feat_nchw, int32_t n, int32_t C, int32_t H, int32_t W, const float* w_in,
                       int32_t ld_w_in, const float* b_in, int32_t Hd, const float* empty_feature_or_null, float* G_out,
@@ -186,6 +193,64 @@ int bts_query_field(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg
     e = bts::launch_general(p, true, reinterpret_cast<cudaStream_t>(stream));
   }
   if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_query_field: %s", cudaGetErrorString(e));
+  return BTS_OK;
+}
+
+int bts_fold_features_bwd(const float* d_G, const float* feat_nchw, int32_t n, int32_t C, int32_t H, int32_t W,
+                          const float* w_in, int32_t ld, int32_t Hd, float* d_feat_or_null, float* d_w_f, float* d_b_in,
+                          bts_stream_t stream) {
+  if (!d_G || !feat_nchw || !w_in || !d_w_f || !d_b_in) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_fold_features_bwd: null pointer");
+  if (n < 1 || C < 1 || H < 1 || W < 1 || Hd < 1 || ld < C) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_fold_features_bwd: bad sizes");
+  const int64_t HW = (int64_t)H * W;
+  if (!bts::fold_bwd_tc_supported(d_G, feat_nchw, d_feat_or_null, C, HW, Hd))
+    return fail(BTS_ERR_UNSUPPORTED, "bts_fold_features_bwd: needs C in {32,64}, d_hidden in {32,64}, H*W %% 4 == 0 and 16-byte "
+                "aligned tensors (got C=%d, d_hidden=%d, H*W=%lld)", C, Hd, (long long)HW);
+  const cudaError_t e = bts::launch_fold_bwd_tc(d_G, feat_nchw, n, C, HW, w_in, ld, Hd, d_feat_or_null, d_w_f, d_b_in,
+                                                reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_fold_features_bwd: %s", cudaGetErrorString(e));
+  return BTS_OK;
+}
+
+static int patch_loss_check(const char* who, const float* pred, const float* gt, int64_t P, int32_t h, int32_t w,
+                            int32_t nv, int32_t c) {
+  if (!pred || !gt) return fail(BTS_ERR_INVALID_ARGUMENT, "%s: null pred / gt", who);
+  if (P < 0) return fail(BTS_ERR_INVALID_ARGUMENT, "%s: negative patch count", who);
+  if (!bts::patch_loss_supported(h, w, nv, c))
+    return fail(BTS_ERR_UNSUPPORTED, "%s: patch %dx%d, %d views, %d channels (limits: side <= 16, views <= 16, channels <= 4)", who, h, w, nv, c);
+  return BTS_OK;
+}
+
+int bts_patch_loss_fwd(const float* pred, const float* gt, const float* invalid_ray_or_null,
+                       const float* invalid_mass_or_null, float mass_thresh, int64_t P, int32_t h, int32_t w, int32_t nv,
+                       int32_t c, float* per_ray, int32_t* argmin_or_null, float* errors_or_null, bts_stream_t stream) {
+  int rc = patch_loss_check("bts_patch_loss_fwd", pred, gt, P, h, w, nv, c);
+  if (rc != BTS_OK) return rc;
+  if (!per_ray) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_patch_loss_fwd: per_ray is null");
+  if (P == 0) return BTS_OK;
+  bts::PatchLossParams p;
+  memset(&p, 0, sizeof(p));
+  p.pred = pred; p.gt = gt; p.invalid_ray = invalid_ray_or_null; p.invalid_mass = invalid_mass_or_null;
+  p.mass_thresh = mass_thresh; p.P = P; p.h = h; p.w = w; p.nv = nv; p.c = c;
+  p.per_ray = per_ray; p.argmin = argmin_or_null; p.errors = errors_or_null;
+  const cudaError_t e = bts::launch_patch_loss(p, false, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_patch_loss_fwd: %s", cudaGetErrorString(e));
+  return BTS_OK;
+}
+
+int bts_patch_loss_bwd(const float* pred, const float* gt, const float* invalid_ray_or_null,
+                       const float* invalid_mass_or_null, float mass_thresh, int64_t P, int32_t h, int32_t w, int32_t nv,
+                       int32_t c, const int32_t* argmin, const float* g_per_ray, float* d_pred, bts_stream_t stream) {
+  int rc = patch_loss_check("bts_patch_loss_bwd", pred, gt, P, h, w, nv, c);
+  if (rc != BTS_OK) return rc;
+  if (!argmin || !g_per_ray || !d_pred) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_patch_loss_bwd: null argmin / g_per_ray / d_pred");
+  if (P == 0) return BTS_OK;
+  bts::PatchLossParams p;
+  memset(&p, 0, sizeof(p));
+  p.pred = pred; p.gt = gt; p.invalid_ray = invalid_ray_or_null; p.invalid_mass = invalid_mass_or_null;
+  p.mass_thresh = mass_thresh; p.P = P; p.h = h; p.w = w; p.nv = nv; p.c = c;
+  p.argmin = const_cast<int32_t*>(argmin); p.g_per_ray = g_per_ray; p.d_pred = d_pred;
+  const cudaError_t e = bts::launch_patch_loss(p, true, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_patch_loss_bwd: %s", cudaGetErrorString(e));
   return BTS_OK;
 }
 

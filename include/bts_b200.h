@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BTS_ABI_VERSION 6
+#define BTS_ABI_VERSION 7
 #define BTS_MAX_BLOCKS 8   /* ResnetFC blocks supported by the kernels */
 
 typedef struct CUstream_st* bts_stream_t; /* == cudaStream_t */
@@ -192,6 +192,36 @@ int bts_render_bwd(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg*
 int bts_query_field(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg* cfg, const float* xyz, int64_t n,
                     int64_t P, float* sigma, float* invalid_f, float* rgb_or_null, float* invalid_or_null,
                     bts_stream_t stream);
+
+/* Backward of bts_fold_features (the dense tail of bts_render_bwd): given d_G (n, H, W, Hd) accumulated by
+ * bts_render_bwd,  d_feat (n, C, H, W) = W_F^T d_G  (written; NULL when the encoder is frozen),
+ * d_w_f (Hd, C) += d_G^T F  and  d_b_in (Hd) += sum d_G  (both ACCUMULATED: zero them first).  This is the lin_in part of
+ * what torch autograd does in loss.backward() (utils/base_trainer.py:297; models/common/model/resnetfc.py:88,147).
+ * Tensor-core path only: C in {32, 64}, Hd in {32, 64}, H*W % 4 == 0, 16-byte aligned tensors; anything else returns
+ * BTS_ERR_UNSUPPORTED and the caller keeps its own dense formulation. */
+int bts_fold_features_bwd(const float* d_G, const float* feat_nchw, int32_t n, int32_t C, int32_t H, int32_t W,
+                          const float* w_in, int32_t ld, int32_t Hd, float* d_feat_or_null, float* d_w_f, float* d_b_in,
+                          bts_stream_t stream);
+
+/* Patch photometric loss of the training step: replaces compute_errors_l1ssim (models/bts/model/loss.py:10-18, SSIM of
+ * models/common/model/layers.py:79-150 with zero padding, 3x3 gaussian window, comp_mode) and the reduction of
+ * ReconstructionLoss.__call__ (loss.py:151-167): per ray 0.85 * mean_c(clamp(1 - SSIM, 0, 1) / 2) + 0.15 * mean_c|x - y|,
+ * minimum over the nv rendered views, times (1 - invalid ray).
+ *   pred (P, h, w, nv, c): the renderer's rgb output in patch order (PatchRaySampler.reconstruct, ray_sampler.py:164-200)
+ *   gt   (P, h, w, c);  invalid_ray (P, h, w) 0/1 or NULL;  alternatively invalid_mass (P, h, w, nv) (BtsRenderOut.invalid_mass)
+ *   with the "weight_guided" rule invalid = all_v(mass_v > mass_thresh) (loss.py:105-108) applied in the kernel.
+ * Outputs: per_ray (P, h, w) (its mean is the reference's rgb_loss), argmin (P, h, w) view index (needed by the backward;
+ * may be NULL), errors (P, h, w, nv) un-reduced criterion or NULL. */
+int bts_patch_loss_fwd(const float* pred, const float* gt, const float* invalid_ray_or_null,
+                       const float* invalid_mass_or_null, float mass_thresh, int64_t P, int32_t h, int32_t w, int32_t nv,
+                       int32_t c, float* per_ray, int32_t* argmin_or_null, float* errors_or_null, bts_stream_t stream);
+
+/* Gradient of per_ray with respect to pred: d_pred (P, h, w, nv, c) is fully written (zero for views that do not attain the
+ * minimum and for invalid rays); g_per_ray (P, h, w) is the upstream gradient (1 / numel for the plain mean).  Ties in the
+ * view minimum send the gradient to the first minimal view (torch.amin splits it; ties have measure zero). */
+int bts_patch_loss_bwd(const float* pred, const float* gt, const float* invalid_ray_or_null,
+                       const float* invalid_mass_or_null, float mass_thresh, int64_t P, int32_t h, int32_t w, int32_t nv,
+                       int32_t c, const int32_t* argmin, const float* g_per_ray, float* d_pred, bts_stream_t stream);
 
 /* Name of the kernel family the last bts_render_fwd on this thread dispatched to ("general" | "tc"), for tests. */
 const char* bts_last_kernel(void);

@@ -165,5 +165,30 @@ def main():
               f"-> {os.path.getsize(path) / 1e3:.0f} kB")
 
 
+def make_loss_golden(ref):
+    """Patch photometric loss fixture from the reference's own functions (models/bts/model/loss.py)."""
+    import importlib
+    loss_mod = importlib.import_module("models.bts.model.loss")
+    g = torch.Generator().manual_seed(77)
+    n, pc, h, w, nv, c = 2, 6, 8, 8, 2, 3
+    gt = torch.rand((n, pc, h, w, c), generator=g)
+    pred = (gt.unsqueeze(-2) + 0.15 * torch.randn((n, pc, h, w, nv, c), generator=g)).clamp(0, 1)
+    pred[0, 0] = gt[0, 0].unsqueeze(-2)                       # a perfectly reconstructed patch (SSIM clamp active)
+    pred[0, 1, :, :, 0] = 0.0                                 # a black view
+    invalid = torch.rand((n, pc, h, w), generator=g) > 0.8
+    pred = pred.clone().requires_grad_(True)
+    errors = loss_mod.compute_errors_l1ssim(pred, gt.unsqueeze(-2))            # (n,pc,h,w,nv,1)   loss.py:154
+    per_ray = errors.amin(-2) * (1 - invalid.unsqueeze(-1).to(torch.float32))   # :155, :160-161
+    loss = per_ray.mean()                                                       # :166
+    loss.backward()
+    os.makedirs(os.path.join(GOLDEN_DIR, "loss"), exist_ok=True)
+    path = os.path.join(GOLDEN_DIR, "loss", "l1ssim.npz")
+    np.savez_compressed(path, pred=pred.detach().numpy(), gt=gt.numpy(), invalid=invalid.numpy(),
+                        errors=errors.detach().numpy(), per_ray=per_ray.detach().numpy(), loss=loss.detach().numpy(),
+                        grad_pred=pred.grad.numpy())
+    print(f"loss_l1ssim: loss {loss.item():.6f} -> {os.path.getsize(path) / 1e3:.0f} kB")
+
+
 if __name__ == "__main__":
     main()
+    make_loss_golden(ref_import.load_reference())

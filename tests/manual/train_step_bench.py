@@ -16,11 +16,18 @@ net, wrapped = syn.build_model(wl, dev, state_dict=sd)
 net.encoder.feats.requires_grad_(True)
 imgs, Ks, poses, rays, u = (t.to(dev) for t in (wl.images, wl.Ks, wl.poses_c2w, wl.rays, wl.u))
 wants = dict(want_weights=True, want_alphas=True, want_rgb_samps=True)   # models/bts/trainer.py:245
+LOSS = os.environ.get("LOSS", "probe")      # "l1ssim": the reference's photometric patch loss on both arms
+rgb_gt = torch.rand((n, R, 3), generator=torch.Generator().manual_seed(9)).to(dev)
 
 
 def ours():
     net.zero_grad(set_to_none=True)
     net.encode(imgs, Ks, poses, ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
+    if LOSS == "l1ssim":
+        from behindthescenes_b200.loss import patch_photometric_loss
+        out = wrapped(rays, u=u, want_weights=True, want_alphas=True, want_invalid=False, want_invalid_mass=True)["coarse"]
+        patch_photometric_loss(out["rgb"], rgb_gt, invalid_mass=out["invalid_mass"], patch=(8, 8))[0].backward()
+        return
     out = wrapped(rays, u=u, **wants)["coarse"]
     gu.probe_loss(out).backward()
 
@@ -38,7 +45,10 @@ def timeit(fn, steps=10, warm=3):
     return a.elapsed_time(b) / steps
 
 
-ms_ours = timeit(ours)
+ms_ours = timeit(ours, steps=int(os.environ.get("STEPS", 10)), warm=int(os.environ.get("WARM", 3)))
+if os.environ.get("ONLY_OURS"):          # launch-list runs under ncu
+    print(json.dumps({"ms_ours": ms_ours, "loss": LOSS}))
+    sys.exit(0)
 # reference op chain with autograd on the GPU
 from oracle import bts_oracle as orc
 from tests.golden_io import mlp_params
@@ -53,12 +63,17 @@ def ref():
         t.grad = None
     st = orc.encode_state(imgs, Ks, poses, feats_g, wl.ids_encoder, wl.ids_render)
     out = orc.render(st, mlp_params(sdg), fcfg, rcfg, rays, u=u, empty_feature=sdg.get("empty_feature"), **wants)["coarse"]
+    if LOSS == "l1ssim":
+        from oracle import loss_oracle as lo
+        inv = ((out["invalid"].to(torch.float32) * out["weights"].unsqueeze(-1)).sum(-2) > .9).all(-1)      # loss.py:107
+        lo.patch_loss(out["rgb"].view(n, R // 64, 8, 8, -1, 3), rgb_gt.view(n, R // 64, 8, 8, 3), inv.view(n, R // 64, 8, 8))[0].backward()
+        return
     gu.probe_loss(out).backward()
 
 
 ms_ref = timeit(ref, steps=5, warm=2)
 g_ours = net.mlp_coarse.lin_in.weight.grad.detach().clone()
 g_ref = sdg["mlp_coarse.lin_in.weight"].grad
-print(json.dumps({"workload": f"cfg3-shaped training step: n={n} frames {H}x{W}, {R} rays each, K=64, Vc=2, fwd+bwd of the render path (encoder excluded)",
+print(json.dumps({"workload": f"cfg3-shaped training step: n={n} frames {H}x{W}, {R} rays each, K=64, Vc=2, fwd+bwd of the render path (encoder excluded), loss=" + LOSS,
                   "ms_ours": ms_ours, "ms_reference_eager_gpu": ms_ref, "speedup": ms_ref / ms_ours,
                   "rays_per_s_ours": n * R / ms_ours * 1e3, "grad_rel_err_lin_in": gu.rel_err(g_ours.cpu(), g_ref.cpu())}))

@@ -65,3 +65,51 @@ def test_fold_of_values_that_stress_the_tf32_split():
     err = (G.double().cpu() - ref).abs()
     bound = 4e-6 * torch.einsum("kc,nchw->nhwk", w_in[:, :C].abs().double(), feat.abs().double()) + 1e-30
     assert (err <= bound).all()
+
+
+def _fold_bwd(dG, feat, w_in, Hd, want_df=True):
+    lib = _lib.load()
+    n, C, H, W = feat.shape
+    d_feat = torch.full_like(feat, float("nan")) if want_df else None
+    d_wf = torch.zeros((Hd, C), device="cuda")
+    d_b = torch.zeros((Hd,), device="cuda")
+    rc = lib.bts_fold_features_bwd(dG.data_ptr(), feat.data_ptr(), n, C, H, W, w_in.data_ptr(), w_in.shape[1], Hd,
+                                   None if d_feat is None else d_feat.data_ptr(), d_wf.data_ptr(), d_b.data_ptr(),
+                                   torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return rc, d_feat, d_wf, d_b
+
+
+@pytest.mark.parametrize("n,C,Hd,H,W", [(2, 64, 64, 192, 640), (3, 64, 64, 13, 20), (1, 64, 32, 25, 36), (2, 32, 64, 8, 16),
+                                        (1, 32, 32, 3, 4), (5, 64, 64, 64, 157 * 4)])
+def test_fold_backward_matches_fp64(n, C, Hd, H, W):
+    """bts_fold_features_bwd (3xTF32 tcgen05, hi/lo halves stacked along M) vs fp64 einsums, incl. ragged last tiles
+    (H*W % 64 != 0), more tiles than SMs and fewer tiles than SMs."""
+    g = torch.Generator().manual_seed(n * 77 + C + Hd + H)
+    feat = (torch.randn((n, C, H, W), generator=g) * 2).cuda()
+    w_in = torch.randn((Hd, C + 39), generator=g).cuda()
+    dG = torch.randn((n, H, W, Hd), generator=g).cuda()
+    dG[:, ::3] = 0                                                  # the real dG is sparse: rows no ray touched
+    rc, d_feat, d_wf, d_b = _fold_bwd(dG, feat, w_in, Hd)
+    assert rc == 0, _lib.load().bts_last_error()
+    assert _lib.load().bts_debug_tc_timeouts() == 0
+    W_F = w_in[:, :C].double()
+    ref_df = torch.einsum("nhwk,kc->nchw", dG.double(), W_F)
+    ref_wf = torch.einsum("nhwk,nchw->kc", dG.double(), feat.double())
+    ref_b = dG.double().sum((0, 1, 2))
+    assert torch.isfinite(d_feat).all()
+    assert (d_feat.double() - ref_df).abs().max().item() <= 3e-6 * ref_df.abs().max().item()
+    # the K = n*H*W reductions: error relative to the sum of magnitudes (fp32 accumulation of up to 2M terms)
+    mag_wf = torch.einsum("nhwk,nchw->kc", dG.abs().double(), feat.abs().double())
+    assert ((d_wf.double() - ref_wf).abs() <= 2e-6 * mag_wf + 1e-30).all()
+    assert ((d_b.double() - ref_b).abs() <= 2e-6 * dG.abs().double().sum((0, 1, 2)) + 1e-30).all()
+    # frozen encoder: no dF, same weight gradients (up to atomic ordering)
+    rc2, none, d_wf2, d_b2 = _fold_bwd(dG, feat, w_in, Hd, want_df=False)
+    assert rc2 == 0 and none is None
+    assert ((d_wf2 - d_wf).abs().double() <= 1e-6 * mag_wf + 1e-30).all()
+
+
+def test_fold_backward_unsupported_shapes_are_reported():
+    feat = torch.randn((1, 48, 8, 8)).cuda()
+    rc, *_ = _fold_bwd(torch.randn((1, 8, 8, 64)).cuda(), feat, torch.randn((64, 48 + 39)).cuda(), 64)
+    assert rc == -2 and b"bts_fold_features_bwd" in _lib.load().bts_last_error()

@@ -1,0 +1,35 @@
+"""CPU: the loss oracle (oracle/loss_oracle.py) against the fixture the unmodified reference loss functions produced
+(tests/golden/loss/l1ssim.npz, oracle/make_goldens.py::make_loss_golden)."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import loss_oracle as lo
+
+FIX = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loss", "l1ssim.npz")
+
+
+def load_loss_fixture():
+    z = np.load(FIX)
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def test_oracle_matches_reference_errors_loss_and_gradient():
+    f = load_loss_fixture()
+    pred = f["pred"].clone().requires_grad_(True)
+    errors = lo.errors_l1ssim(pred, f["gt"].unsqueeze(-2))
+    assert errors.shape == f["errors"].shape
+    assert torch.equal(errors.detach(), f["errors"])           # same torch ops, same machine family: bit-exact
+    loss, per_ray = lo.patch_loss(pred, f["gt"], f["invalid"])
+    assert abs(loss.item() - float(f["loss"])) < 1e-8
+    assert torch.allclose(per_ray.detach().unsqueeze(-1), f["per_ray"], atol=1e-8)
+    loss.backward()
+    assert torch.allclose(pred.grad, f["grad_pred"], atol=1e-9)
+
+
+def test_fixture_covers_the_edge_cases():
+    f = load_loss_fixture()
+    assert (f["errors"][0, 0] == 0).all()                      # perfectly reconstructed patch: SSIM clamp at 0
+    assert f["invalid"].any() and not f["invalid"].all()
+    assert (f["per_ray"].squeeze(-1)[f["invalid"]] == 0).all()
