@@ -14,8 +14,12 @@
 // reduced into global memory with one atomicAdd per element per CTA at the end.
 // Reference: this is the part of loss.backward() (utils/base_trainer.py:297) that differentiates ResnetFC.lin_in
 // (models/common/model/resnetfc.py:88,147) with respect to the sampled encoder features and its weights.
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 #include "tcgen05.cuh"
+#include "tensor_map.cuh"
 
 namespace bts {
 
@@ -23,9 +27,12 @@ __device__ int g_fold_bwd_barrier_timeouts = 0;
 
 namespace foldbwd {
 
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;
 constexpr int kTile = 64;            // pixels per tile
-constexpr int kPad = 4;              // floats of row padding in the raw staging tiles (bank-conflict-free transposes)
+constexpr int kPad = 4;              // floats of row padding in the row-exchange buffer
+// The raw staging tiles are dense (one bulk copy for the contiguous dG tile, one tensor-map copy for the F tile); the
+// transposes below walk them diagonally (chunk index offset by the row index) so that every quarter-warp touches eight
+// distinct 16-byte bank groups on both the read and the write side.
 
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(smem_dst)),
@@ -42,8 +49,8 @@ struct L {
   static_assert(HD == 32 || HD == 64, "stacked hi/lo rows need Hd <= 64");
   static_assert(C == 32 || C == 64, "stacked hi/lo rows need C <= 64");
   static constexpr int kN2 = C + 16;                                // GEMM 2 columns: C features + the ones column (+ padding to 16)
-  static constexpr int kRawGRow = (HD + kPad) * 4;                  // bytes per staged dG row
-  static constexpr int kRawFRow = (kTile + kPad) * 4;               // bytes per staged F row
+  static constexpr int kRawGRow = HD * 4;                           // bytes per staged dG row (dense)
+  static constexpr int kRawFRow = kTile * 4;                        // bytes per staged F row (dense)
   static constexpr int kRawG = kTile * kRawGRow;
   static constexpr int kRawF = C * kRawFRow;
   static constexpr int kB1 = (HD / 4) * kTile * 16;                 // dG^T, K = hidden unit: [Hd/4 chunks][64 px rows][16 B]
@@ -72,7 +79,8 @@ template <int HD, int C>
 __global__ void __launch_bounds__(kThreads, 1) fold_bwd_tc_kernel(const float* __restrict__ dG, const float* __restrict__ feat,
                                                                    int64_t HW, int n_batches, const float* __restrict__ w_in,
                                                                    int ld, float* __restrict__ d_feat, float* __restrict__ d_wf,
-                                                                   float* __restrict__ d_b) {
+                                                                   float* __restrict__ d_b,
+                                                                   const __grid_constant__ CUtensorMap feat_map, int use_map) {
   using Lt = L<HD, C>;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -107,36 +115,43 @@ __global__ void __launch_bounds__(kThreads, 1) fold_bwd_tc_kernel(const float* _
   __syncthreads();
   tc::tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // TMEM lanes of this warp
+  const int trow = (warp & 3) * 32 + lane, thalf = warp >> 2;              // accumulator row / column half this thread reads
   const uint32_t idesc1 = tc::instr_desc(tc::kFmtTF32, 128, kTile);
   const uint32_t idesc2 = tc::instr_desc(tc::kFmtTF32, 128, Lt::kN2);
 
   const int64_t tiles_per_b = (HW + kTile - 1) / kTile;
   const int64_t n_tiles = tiles_per_b * n_batches;
-  auto issue_load = [&](int64_t tile, int buf) {          // warp 0: one expect_tx, then the row copies spread over the lanes
+  auto issue_load = [&](int64_t tile, int buf) {          // one elected thread: the dG tile is contiguous, the F tile one box
     const int64_t b = tile / tiles_per_b, p0 = (tile % tiles_per_b) * kTile;
     const int valid = (int)((HW - p0) < kTile ? (HW - p0) : kTile);
-    if (lane == 0) mbar_expect_tx(&full[buf], (uint32_t)valid * HD * 4u + (uint32_t)C * valid * 4u);
-    __syncwarp();
-    const float* gsrc = dG + ((size_t)b * HW + p0) * HD;
     unsigned char* gdst = smem + Lt::kOffRawG + buf * Lt::kRawG;
-    for (int r = lane; r < valid; r += 32) bulk_load(gdst + r * Lt::kRawGRow, gsrc + (size_t)r * HD, HD * 4u, &full[buf]);
-    const float* fsrc = feat + ((size_t)b * C) * HW + p0;
     unsigned char* fdst = smem + Lt::kOffRawF + buf * Lt::kRawF;
-    for (int c = lane; c < C; c += 32) bulk_load(fdst + c * Lt::kRawFRow, fsrc + (size_t)c * HW, (uint32_t)valid * 4u, &full[buf]);
+    const uint32_t g_bytes = (uint32_t)valid * HD * 4u;
+    if (use_map) {
+      mbar_expect_tx(&full[buf], g_bytes + (uint32_t)Lt::kRawF);
+      bulk_load(gdst, dG + ((size_t)b * HW + p0) * HD, g_bytes, &full[buf]);
+      tmap::load_tile_3d(fdst, &feat_map, (int)p0, 0, (int)b, &full[buf]);
+    } else {
+      mbar_expect_tx(&full[buf], g_bytes + (uint32_t)C * valid * 4u);
+      bulk_load(gdst, dG + ((size_t)b * HW + p0) * HD, g_bytes, &full[buf]);
+      const float* fsrc = feat + ((size_t)b * C) * HW + p0;
+      for (int c = 0; c < C; ++c) bulk_load(fdst + c * Lt::kRawFRow, fsrc + (size_t)c * HW, (uint32_t)valid * 4u, &full[buf]);
+    }
   };
 
   bool dead = false;                                       // bounded waits (bug guard), see render_tc.cu
   uint32_t full_phase[2] = {0, 0}, mma_phase = 0;
   int64_t tile = blockIdx.x;
-  if (warp == 0 && tile < n_tiles) issue_load(tile, 0);
+  if (tid == 0 && use_map) tmap::prefetch_map(&feat_map);
+  if (tid == 0 && tile < n_tiles) issue_load(tile, 0);
   int buf = 0;
   bool first = true;
   float* ex = reinterpret_cast<float*>(smem + Lt::kOffEx);
   constexpr int kExF = kTile + kPad;
   for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
     const int64_t next = tile + gridDim.x;
-    if (warp == 0 && next < n_tiles) issue_load(next, buf ^ 1);             // raw[buf^1] was consumed one iteration ago
+    if (tid == 0 && next < n_tiles) issue_load(next, buf ^ 1);             // raw[buf^1] was consumed one iteration ago
     const int64_t b = tile / tiles_per_b, p0 = (tile % tiles_per_b) * kTile;
     const int valid = (int)((HW - p0) < kTile ? (HW - p0) : kTile);
 
@@ -146,9 +161,11 @@ __global__ void __launch_bounds__(kThreads, 1) fold_bwd_tc_kernel(const float* _
     const unsigned char* rawf = smem + Lt::kOffRawF + buf * Lt::kRawF;
     // ---- (a) dG^T with K = hidden unit (GEMM 1's B): thread = pixel row, 16-byte chunks of its dG row ----
     if (want_df) {
-      const int p = tid % kTile;
-#pragma unroll 4
-      for (int kc = tid / kTile; kc < HD / 4; kc += kThreads / kTile) {
+      const int p = tid % kTile, r = tid / kTile;
+      constexpr int kChunks = HD / 4, kRows = kThreads / kTile;
+#pragma unroll
+      for (int it = 0; it < kChunks / kRows; ++it) {
+        const int kc = (p + kRows * it + r) % kChunks;                        // diagonal walk
         float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p < valid) f = *reinterpret_cast<const float4*>(rawg + p * Lt::kRawGRow + kc * 16);
         const float4 h = make_float4(tf32_hi(f.x), tf32_hi(f.y), tf32_hi(f.z), tf32_hi(f.w));
@@ -174,9 +191,11 @@ __global__ void __launch_bounds__(kThreads, 1) fold_bwd_tc_kernel(const float* _
     }
     // ---- (c) F with K = pixel (GEMM 2's B): thread = channel row, 16-byte chunks of its F row ----
     {
-      const int c = tid % C;
-#pragma unroll 4
-      for (int pc = tid / C; pc < kTile / 4; pc += kThreads / C) {
+      const int c = tid % C, r = tid / C;
+      constexpr int kChunks = kTile / 4, kRows = kThreads / C;
+#pragma unroll
+      for (int it = 0; it < kChunks / kRows; ++it) {
+        const int pc = (c + kRows * it + r) % kChunks;                        // diagonal walk
         float4 f = *reinterpret_cast<const float4*>(rawf + c * Lt::kRawFRow + pc * 16);
         if (pc * 4 + 0 >= valid) f.x = 0.f;
         if (pc * 4 + 1 >= valid) f.y = 0.f;
@@ -220,30 +239,33 @@ __global__ void __launch_bounds__(kThreads, 1) fold_bwd_tc_kernel(const float* _
     tc::tc_fence_after_sync();
     // ---- epilogue: dF[c, px] = D1[c, px] + D1[64 + c, px], stored as rows of the NCHW gradient ----
     if (want_df) {
-      float row[kTile];
+      constexpr int kHalf = kTile / 2;                       // warps 0-3 read columns [0, 32), warps 4-7 columns [32, 64)
+      float row[kHalf];
 #pragma unroll
-      for (int c0 = 0; c0 < kTile; c0 += 16) {
+      for (int c0 = 0; c0 < kHalf; c0 += 16) {
         uint32_t v[16];
-        tc::tmem_ld_x16(t_lane + c0, v);
+        tc::tmem_ld_x16(t_lane + thalf * kHalf + c0, v);
         tc::tmem_ld_wait();
 #pragma unroll
         for (int e = 0; e < 16; ++e) row[c0 + e] = __uint_as_float(v[e]);
       }
-      if (tid >= 64 && tid - 64 < C) {
+      float* exr = ex + (trow & 63) * kExF + thalf * kHalf;
+      if (trow >= 64 && trow - 64 < C) {
 #pragma unroll
-        for (int e = 0; e < kTile; e += 4) *reinterpret_cast<float4*>(ex + (tid - 64) * kExF + e) = make_float4(row[e], row[e + 1], row[e + 2], row[e + 3]);
+        for (int e = 0; e < kHalf; e += 4) *reinterpret_cast<float4*>(exr + e) = make_float4(row[e], row[e + 1], row[e + 2], row[e + 3]);
       }
       __syncthreads();
-      if (tid < C) {
+      if (trow < C) {
 #pragma unroll
-        for (int e = 0; e < kTile; e += 4) {
-          float4 o = *reinterpret_cast<float4*>(ex + tid * kExF + e);
+        for (int e = 0; e < kHalf; e += 4) {
+          float4 o = *reinterpret_cast<float4*>(exr + e);
           o.x += row[e]; o.y += row[e + 1]; o.z += row[e + 2]; o.w += row[e + 3];
-          *reinterpret_cast<float4*>(ex + tid * kExF + e) = o;
+          *reinterpret_cast<float4*>(exr + e) = o;
         }
       }
       __syncthreads();
       float* dst = d_feat + ((size_t)b * C) * HW + p0;
+#pragma unroll 4
       for (int i = tid; i < C * (kTile / 4); i += kThreads) {
         const int c = i / (kTile / 4), seg = i % (kTile / 4);
         if (seg * 4 < valid) *reinterpret_cast<float4*>(dst + (size_t)c * HW + seg * 4) = *reinterpret_cast<const float4*>(ex + c * kExF + seg * 4);
@@ -256,17 +278,19 @@ __global__ void __launch_bounds__(kThreads, 1) fold_bwd_tc_kernel(const float* _
   tc::tc_fence_after_sync();
   {
     float row[Lt::kN2];
+    if (warp < 4) {
 #pragma unroll
-    for (int c0 = 0; c0 < Lt::kN2; c0 += 16) {
-      uint32_t v[16];
-      tc::tmem_ld_x16(t_lane + 64 + c0, v);
-      tc::tmem_ld_wait();
+      for (int c0 = 0; c0 < Lt::kN2; c0 += 16) {
+        uint32_t v[16];
+        tc::tmem_ld_x16(t_lane + 64 + c0, v);
+        tc::tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 16; ++e) row[c0 + e] = __uint_as_float(v[e]);
-    }
-    if (tid >= 64 && tid - 64 < HD) {
+        for (int e = 0; e < 16; ++e) row[c0 + e] = __uint_as_float(v[e]);
+      }
+      if (tid >= 64 && tid - 64 < HD) {
 #pragma unroll
-      for (int e = 0; e <= C; ++e) ex[(tid - 64) * kExF + e] = row[e];
+        for (int e = 0; e <= C; ++e) ex[(tid - 64) * kExF + e] = row[e];
+      }
     }
     __syncthreads();
     if (tid < HD) {
@@ -301,7 +325,11 @@ static cudaError_t launch_fold_bwd_t(const float* dG, const float* feat, int n, 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t n_tiles = ((HW + foldbwd::kTile - 1) / foldbwd::kTile) * n;
   const int grid = (int)(n_tiles < sms ? n_tiles : sms);
-  kern<<<grid, foldbwd::kThreads, Lt::kSmemBytes, stream>>>(dG, feat, HW, n, w_in, ld, d_feat, d_wf, d_b);
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  const char* rows = getenv("BTS_FOLD_TMA_ROWS");            // tests: force the row-copy loads
+  const int use_map = !(rows && rows[0] == '1') && tmap::make_feature_map(&map, feat, n, C, HW, foldbwd::kTile) ? 1 : 0;
+  kern<<<grid, foldbwd::kThreads, Lt::kSmemBytes, stream>>>(dG, feat, HW, n, w_in, ld, d_feat, d_wf, d_b, map, use_map);
   return cudaGetLastError();
 }
 

@@ -2,8 +2,9 @@
 //
 // Per 128-pixel tile (M = 128 pixels, N = Hd, K = C):
 //   * the raw feature tile F[b, 0:C, p0:p0+128] (C rows of 512 B, NCHW) is fetched by the TMA engine with one
-//     cp.async.bulk per channel row into a double-buffered staging area (mbarrier complete_tx), so the loads of tile
-//     i+1 overlap the work on tile i;
+//     cp.async.bulk.tensor box (tensor_map.cuh; one bulk copy per channel row when the driver's tensor-map encoder is
+//     unavailable) into a double-buffered staging area (mbarrier complete_tx), so the loads of tile i+1 overlap the work
+//     on tile i;
 //   * the 128 threads transpose it into the K-major core-matrix layout the MMA reads ([chunk of 4 channels][pixel][16 B])
 //     and split every value into tf32 hi + lo on the way (hi = low 13 mantissa bits cleared, lo = exact residual);
 //   * one thread issues D[128 x Hd] = A_hi W_hi + A_lo W_hi + A_hi W_lo (kind::tf32; the dropped lo*lo term is ~2^-22
@@ -11,8 +12,12 @@
 //   * epilogue: tcgen05.ld of the pixel's row, + bias, 16-byte stores of the 4*Hd contiguous bytes of G.
 // Bound: HBM (C*4 B read + Hd*4 B written per pixel); the CUDA-core kernel in fold.cu stays as the general path
 // (any C, unaligned frames).  Reference tensors: see fold.cu.
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 #include "tcgen05.cuh"
+#include "tensor_map.cuh"
 
 namespace bts {
 
@@ -52,7 +57,8 @@ struct L {
 template <int HD, int C>
 __global__ void __launch_bounds__(kThreads, 1) fold_tc_kernel(const float* __restrict__ feat, int64_t HW, int n_batches,
                                                                const float* __restrict__ w_in, int ld,
-                                                               const float* __restrict__ b_in, float* __restrict__ G) {
+                                                               const float* __restrict__ b_in, float* __restrict__ G,
+                                                               const __grid_constant__ CUtensorMap feat_map, int use_map) {
   using Lt = L<HD, C>;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -88,19 +94,25 @@ __global__ void __launch_bounds__(kThreads, 1) fold_tc_kernel(const float* __res
 
   const int64_t tiles_per_b = (HW + kTile - 1) / kTile;
   const int64_t n_tiles = tiles_per_b * n_batches;
-  auto issue_load = [&](int64_t tile, int buf) {          // one elected thread: C row copies, one expect_tx
+  auto issue_load = [&](int64_t tile, int buf) {          // one elected thread: one tensor-map box (or C row copies)
     const int64_t b = tile / tiles_per_b, p0 = (tile % tiles_per_b) * kTile;
     const int valid = (int)((HW - p0) < kTile ? (HW - p0) : kTile);
+    unsigned char* dst = smem + Lt::kOffRaw + buf * Lt::kRaw;
+    if (use_map) {
+      mbar_expect_tx(&full[buf], (uint32_t)Lt::kRaw);
+      tmap::load_tile_3d(dst, &feat_map, (int)p0, 0, (int)b, &full[buf]);
+      return;
+    }
     const uint32_t row_bytes = (uint32_t)valid * 4u;
     mbar_expect_tx(&full[buf], row_bytes * C);
     const float* src = feat + ((size_t)b * C) * HW + p0;
-    unsigned char* dst = smem + Lt::kOffRaw + buf * Lt::kRaw;
     for (int c = 0; c < C; ++c) bulk_load(dst + c * kTile * 4, src + (size_t)c * HW, row_bytes, &full[buf]);
   };
 
   bool dead = false;                                       // bounded waits (bug guard), see render_tc.cu
   uint32_t full_phase[2] = {0, 0}, mma_phase = 0;
   int64_t tile = blockIdx.x;
+  if (tid == 0 && use_map) tmap::prefetch_map(&feat_map);
   if (tid == 0 && tile < n_tiles) issue_load(tile, 0);
   int buf = 0;
   for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
@@ -189,7 +201,11 @@ static cudaError_t launch_fold_tc_t(const float* feat, int n, int64_t HW, const 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t n_tiles = ((HW + foldtc::kTile - 1) / foldtc::kTile) * n;
   const int grid = (int)(n_tiles < sms ? n_tiles : sms);
-  kern<<<grid, foldtc::kThreads, Lt::kSmemBytes, stream>>>(feat, HW, n, w_in, ld, b_in, G);
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  const char* rows = getenv("BTS_FOLD_TMA_ROWS");            // tests: force the row-copy loads
+  const int use_map = !(rows && rows[0] == '1') && tmap::make_feature_map(&map, feat, n, C, HW, foldtc::kTile) ? 1 : 0;
+  kern<<<grid, foldtc::kThreads, Lt::kSmemBytes, stream>>>(feat, HW, n, w_in, ld, b_in, G, map, use_map);
   return cudaGetLastError();
 }
 

@@ -113,3 +113,22 @@ def test_fold_backward_unsupported_shapes_are_reported():
     feat = torch.randn((1, 48, 8, 8)).cuda()
     rc, *_ = _fold_bwd(torch.randn((1, 8, 8, 64)).cuda(), feat, torch.randn((64, 48 + 39)).cuda(), 64)
     assert rc == -2 and b"bts_fold_features_bwd" in _lib.load().bts_last_error()
+
+
+def test_row_copy_loads_agree_with_tensor_map_loads(monkeypatch):
+    """BTS_FOLD_TMA_ROWS=1 forces the per-row bulk copies (the path used when the driver has no tensor-map encoder):
+    same shared-memory layout, so results are bit-identical for the forward and equal up to atomic order backward."""
+    n, C, Hd, H, W = 2, 64, 64, 25, 36                             # ragged: 900 px = 14 tiles of 64 + 4
+    g = torch.Generator().manual_seed(11)
+    feat = torch.randn((n, C, H, W), generator=g).cuda()
+    w_in = torch.randn((Hd, C + 39), generator=g).cuda()
+    b_in = torch.randn((Hd,), generator=g).cuda()
+    dG = torch.randn((n, H, W, Hd), generator=g).cuda()
+    G_map, _ = _fold(feat, w_in, b_in, Hd)
+    _, df_map, dwf_map, db_map = _fold_bwd(dG, feat, w_in, Hd)
+    monkeypatch.setenv("BTS_FOLD_TMA_ROWS", "1")
+    G_rows, _ = _fold(feat, w_in, b_in, Hd)
+    rc, df_rows, dwf_rows, db_rows = _fold_bwd(dG, feat, w_in, Hd)
+    assert rc == 0 and _lib.load().bts_debug_tc_timeouts() == 0
+    assert torch.equal(G_map, G_rows) and torch.equal(df_map, df_rows)
+    assert torch.allclose(dwf_map, dwf_rows, rtol=1e-5, atol=1e-4) and torch.allclose(db_map, db_rows, rtol=1e-5, atol=1e-4)
