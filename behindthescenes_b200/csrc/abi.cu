@@ -24,6 +24,7 @@ cudaError_t launch_fold_bwd_tc(const float* dG, const float* feat, int n, int C,
                                float* d_feat, float* d_wf, float* d_b, cudaStream_t stream);
 cudaError_t launch_patch_loss(const PatchLossParams& p, bool backward, cudaStream_t stream);
 bool patch_loss_supported(int h, int w, int nv, int c);
+cudaError_t launch_patch_smooth(const PatchLossParams& p, bool backward, cudaStream_t stream);
 cudaError_t launch_pack_images(const float* img, int nv_total, int Cc, int Hc, int Wc, float* out, cudaStream_t stream);
 }  // namespace bts
 
@@ -251,6 +252,38 @@ int bts_patch_loss_bwd(const float* pred, const float* gt, const float* invalid_
   p.argmin = const_cast<int32_t*>(argmin); p.g_per_ray = g_per_ray; p.d_pred = d_pred;
   const cudaError_t e = bts::launch_patch_loss(p, true, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_patch_loss_bwd: %s", cudaGetErrorString(e));
+  return BTS_OK;
+}
+
+int bts_patch_smooth_fwd(const float* depth, const float* gt, const float* invalid_ray_or_null,
+                         const float* invalid_mass_or_null, float mass_thresh, int64_t P, int32_t h, int32_t w, int32_t nv,
+                         int32_t c, float* per_ray, bts_stream_t stream) {
+  int rc = patch_loss_check("bts_patch_smooth_fwd", depth, gt, P, h, w, nv, c);
+  if (rc != BTS_OK) return rc;
+  if (!per_ray) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_patch_smooth_fwd: per_ray is null");
+  if (P == 0) return BTS_OK;
+  bts::PatchLossParams p;
+  memset(&p, 0, sizeof(p));
+  p.pred = depth; p.gt = gt; p.invalid_ray = invalid_ray_or_null; p.invalid_mass = invalid_mass_or_null;
+  p.mass_thresh = mass_thresh; p.P = P; p.h = h; p.w = w; p.nv = nv; p.c = c; p.per_ray = per_ray;
+  const cudaError_t e = bts::launch_patch_smooth(p, false, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_patch_smooth_fwd: %s", cudaGetErrorString(e));
+  return BTS_OK;
+}
+
+int bts_patch_smooth_bwd(const float* depth, const float* gt, const float* invalid_ray_or_null,
+                         const float* invalid_mass_or_null, float mass_thresh, int64_t P, int32_t h, int32_t w, int32_t nv,
+                         int32_t c, const float* g_per_ray, float* d_depth, bts_stream_t stream) {
+  int rc = patch_loss_check("bts_patch_smooth_bwd", depth, gt, P, h, w, nv, c);
+  if (rc != BTS_OK) return rc;
+  if (!g_per_ray || !d_depth) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_patch_smooth_bwd: null g_per_ray / d_depth");
+  if (P == 0) return BTS_OK;
+  bts::PatchLossParams p;
+  memset(&p, 0, sizeof(p));
+  p.pred = depth; p.gt = gt; p.invalid_ray = invalid_ray_or_null; p.invalid_mass = invalid_mass_or_null;
+  p.mass_thresh = mass_thresh; p.P = P; p.h = h; p.w = w; p.nv = nv; p.c = c; p.g_per_ray = g_per_ray; p.d_pred = d_depth;
+  const cudaError_t e = bts::launch_patch_smooth(p, true, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_patch_smooth_bwd: %s", cudaGetErrorString(e));
   return BTS_OK;
 }
 

@@ -168,6 +168,99 @@ __global__ void __launch_bounds__(256) patch_loss_kernel(PatchLossParams p) {
   }
 }
 
+// Edge-aware smoothness of the rendered depth (models/bts/model/loss.py:21-40, masked as in :247-256): per patch
+//   d = 1 / clamp(depth, 1e-3, 80);  d /= mean_patch(d)
+//   e(y, x) = |d(y, x) - d(y, x+1)| exp(-mean_c |I(y, x) - I(y, x+1)|) + |d(y, x) - d(y+1, x)| exp(-mean_c |I(y, x) - I(y+1, x)|)
+// with the terms that would leave the patch dropped; thread = pixel, the patch mean and the backward's sum by block reduction.
+__device__ __forceinline__ float block_sum(float v, float* red, int tid, int nthr) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < (nthr >> 5); ++i) t += red[i];
+  return t;
+}
+
+template <bool kBackward>
+__global__ void __launch_bounds__(256) patch_smooth_kernel(PatchLossParams p) {
+  extern __shared__ float sm[];
+  const int h = p.h, w = p.w, c = p.c;
+  const int n_px = h * w;
+  float* s_d = sm;                 // normalised inverse depth
+  float* s_i = s_d + n_px;         // image, [c][n_px]
+  float* s_gx = s_i + c * n_px;    // backward: upstream * weight * sign of the x / y edge owned by each pixel
+  float* s_gy = s_gx + n_px;
+  float* red = s_gy + n_px;        // 8 floats
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const bool active = tid < n_px;
+  const int y = active ? tid / w : 0, x = active ? tid % w : 0;
+  const float inv_c = 1.0f / (float)c;
+
+  for (int64_t patch = blockIdx.x; patch < p.P; patch += gridDim.x) {
+    const int64_t ray = patch * n_px + tid;
+    float depth = 1.f, inv = 0.f;
+    if (active) {
+      depth = p.pred[ray];                                                   // pred = depth (P, h, w) for this kernel
+      inv = __fdiv_rn(1.f, fminf(fmaxf(depth, 1e-3f), 80.f));                // loss.py:24
+      for (int ch = 0; ch < c; ++ch) s_i[ch * n_px + tid] = p.gt[ray * c + ch];
+    }
+    const float mean = block_sum(inv, red, tid, nthr) / (float)n_px;         // :25
+    const float d = __fdiv_rn(inv, mean);
+    if (active) s_d[tid] = d;
+    __syncthreads();
+    float wx = 0.f, wy = 0.f, ddx = 0.f, ddy = 0.f;
+    if (active) {
+      if (x + 1 < w) {
+        float a = 0.f;
+        for (int ch = 0; ch < c; ++ch) a += fabsf(s_i[ch * n_px + tid] - s_i[ch * n_px + tid + 1]);
+        wx = expf(-(a * inv_c));                                             // :32, :35
+        ddx = d - s_d[tid + 1];                                              // :29
+      }
+      if (y + 1 < h) {
+        float a = 0.f;
+        for (int ch = 0; ch < c; ++ch) a += fabsf(s_i[ch * n_px + tid] - s_i[ch * n_px + tid + w]);
+        wy = expf(-(a * inv_c));                                             // :33, :36
+        ddy = d - s_d[tid + w];                                              // :30
+      }
+    }
+    const float keep = (active && ray_invalid(p, ray)) ? 0.f : 1.f;          // :252-254
+    if (!kBackward) {
+      if (active) p.per_ray[ray] = (fabsf(ddx) * wx + fabsf(ddy) * wy) * keep;   // :38
+    } else {
+      const float up = active ? p.g_per_ray[ray] * keep : 0.f;
+      const float gx = up * wx * (ddx > 0.f ? 1.f : (ddx < 0.f ? -1.f : 0.f));
+      const float gy = up * wy * (ddy > 0.f ? 1.f : (ddy < 0.f ? -1.f : 0.f));
+      if (active) { s_gx[tid] = gx; s_gy[tid] = gy; }
+      __syncthreads();
+      float gd = gx + gy;                                                    // dE/dd of this pixel: its own edges ...
+      if (active && x > 0) gd -= s_gx[tid - 1];                              // ... and the left / upper neighbour's
+      if (active && y > 0) gd -= s_gy[tid - w];
+      const float dot = block_sum(active ? gd * inv : 0.f, red, tid, nthr);
+      if (active) {
+        const float g_inv = __fdiv_rn(gd, mean) - __fdiv_rn(dot, mean * mean * (float)n_px);
+        const bool pass = depth >= 1e-3f && depth <= 80.f;                   // clamp passes the gradient on [min, max]
+        p.d_pred[ray] = pass ? -g_inv * inv * inv : 0.f;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_patch_smooth(const PatchLossParams& p, bool backward, cudaStream_t stream) {
+  const int threads = ((p.h * p.w + 31) / 32) * 32;
+  const size_t smem = (size_t)((3 + p.c) * p.h * p.w + 8) * sizeof(float);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)(p.P < (int64_t)sms * 16 ? p.P : (int64_t)sms * 16);
+  if (backward)
+    patch_smooth_kernel<true><<<grid, threads, smem, stream>>>(p);
+  else
+    patch_smooth_kernel<false><<<grid, threads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_patch_loss(const PatchLossParams& p, bool backward, cudaStream_t stream) {
   const int threads = ((p.h * p.w + 31) / 32) * 32;
   const size_t smem = (size_t)(backward ? 5 : 2) * p.c * (p.h + 2) * (p.w + 2) * sizeof(float);

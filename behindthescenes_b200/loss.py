@@ -93,3 +93,194 @@ def patch_photometric_loss(rgb, rgb_gt, invalid_ray=None, invalid_mass=None, mas
     if want_errors:
         return loss, per_ray, errors.unsqueeze(-1)
     return loss, per_ray
+
+
+class _PatchSmooth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, gt, invalid_ray, invalid_mass, mass_thresh, nv):
+        lib = _lib.load()
+        n, pc, h, w = depth.shape
+        c = gt.shape[-1]
+        per_ray = torch.empty_like(depth)
+        stream = torch.cuda.current_stream(depth.device).cuda_stream
+        _lib.check(lib.bts_patch_smooth_fwd(depth.data_ptr(), gt.data_ptr(),
+                                            invalid_ray.data_ptr() if invalid_ray is not None else None,
+                                            invalid_mass.data_ptr() if invalid_mass is not None else None,
+                                            float(mass_thresh), n * pc, h, w, nv, c, per_ray.data_ptr(), stream),
+                   "bts_patch_smooth_fwd")
+        ctx.save_for_backward(depth, gt, invalid_ray, invalid_mass)
+        ctx.mass_thresh, ctx.nv = float(mass_thresh), nv
+        return per_ray
+
+    @staticmethod
+    def backward(ctx, g_per_ray):
+        depth, gt, invalid_ray, invalid_mass = ctx.saved_tensors
+        lib = _lib.load()
+        n, pc, h, w = depth.shape
+        g = _f32c(g_per_ray)
+        d_depth = torch.empty_like(depth)
+        stream = torch.cuda.current_stream(depth.device).cuda_stream
+        _lib.check(lib.bts_patch_smooth_bwd(depth.data_ptr(), gt.data_ptr(),
+                                            invalid_ray.data_ptr() if invalid_ray is not None else None,
+                                            invalid_mass.data_ptr() if invalid_mass is not None else None,
+                                            ctx.mass_thresh, n * pc, h, w, ctx.nv, gt.shape[-1], g.data_ptr(), d_depth.data_ptr(),
+                                            stream), "bts_patch_smooth_bwd")
+        return d_depth, None, None, None, None, None
+
+
+def patch_edge_aware_smoothness(depth, rgb_gt, invalid_ray=None, invalid_mass=None, mass_thresh=0.9):
+    """Edge-aware smoothness of the rendered depth per ray (``edge_aware_smoothness``, loss.py:21-40, masked as in
+    loss.py:247-256).  ``depth`` (n, pc, h, w), ``rgb_gt`` (n, pc, h, w, c); masks as in ``patch_photometric_loss``.
+    Returns ``(loss_eas, per_ray)`` with ``loss_eas = per_ray.mean()``; differentiable with respect to ``depth``."""
+    if not depth.is_cuda:
+        raise _lib.BtsCudaError("patch_edge_aware_smoothness runs on CUDA tensors only (no CPU fallback)")
+    n, pc, h, w = depth.shape
+    gt = _f32c(rgb_gt.reshape(n, pc, h, w, -1))
+    nv = 1
+    if invalid_ray is not None:
+        invalid_ray, invalid_mass = _f32c(invalid_ray.reshape(n, pc, h, w)), None
+    elif invalid_mass is not None:
+        nv = invalid_mass.shape[-1]
+        invalid_mass = _f32c(invalid_mass.reshape(n, pc, h, w, nv))
+    per_ray = _PatchSmooth.apply(_f32c(depth), gt, invalid_ray, invalid_mass, mass_thresh, nv)
+    return per_ray.mean(), per_ray
+
+
+class ReconstructionLoss:
+    """Drop-in for ``models.bts.model.loss.ReconstructionLoss`` (loss.py:43-293) on the configurations the reference ships
+    (``criterion: "l1+ssim"``, ``invalid_policy: weight_guided``, ``lambda_edge_aware_smoothness``; every
+    ``configs/exp_*.yaml``): same constructor, same ``loss, loss_dict = criterion(data)`` contract (``utils/base_trainer.py:292``),
+    same ``data`` layout (``data["coarse"][scale]`` / ``data["fine"][scale]`` dicts after ``PatchRaySampler.reconstruct``,
+    ``data["rgb_gt"]``).  The photometric term and the smoothness term are one fused launch each way; the small
+    regularisers (entropy, depth / alpha / surfaceness) stay torch expressions on the per-ray tensors.
+
+    Like the reference, a ``fine`` dict that is just a copy of ``coarse`` (``models/bts/trainer.py:246-247``) is scored a second
+    time with ``lambda_fine`` -- when it holds the same ``rgb`` tensor the coarse result is reused instead of recomputed.
+    ``coarse["invalid_mass"]`` (n, pc, h, w, nv) from ``want_invalid_mass=True`` replaces ``invalid``/``weights`` for the
+    weight-guided policy.  ``criterion`` other than ``"l1+ssim"``, automasking, median thresholding and
+    ``weight_guided_diverse`` raise ``NotImplementedError``."""
+
+    def __init__(self, config, use_automasking=False):
+        self.criterion_str = config.get("criterion", "l2")
+        self.invalid_policy = config.get("invalid_policy", "strict")
+        if self.invalid_policy not in ("strict", "weight_guided", "weight_guided_diverse", None, "none"):
+            raise ValueError(f"unknown invalid_policy {self.invalid_policy!r}")
+        self.ignore_invalid = self.invalid_policy is not None and self.invalid_policy != "none"
+        self.lambda_coarse = config.get("lambda_coarse", 1)
+        self.lambda_fine = config.get("lambda_fine", 1)
+        self.use_automasking = use_automasking
+        self.lambda_entropy = config.get("lambda_entropy", 0)
+        self.lambda_depth_reg = config.get("lambda_depth_reg", 0)
+        self.lambda_alpha_reg = config.get("lambda_alpha_reg", 0)
+        self.lambda_surfaceness_reg = config.get("lambda_surfaceness_reg", 0)
+        self.lambda_edge_aware_smoothness = config.get("lambda_edge_aware_smoothness", 0)
+        self.lambda_depth_smoothness = config.get("lambda_depth_smoothness", 0)
+        self.median_thresholding = config.get("median_thresholding", False)
+        self.alpha_reg_reduction = config.get("alpha_reg_reduction", "ray")
+        self.alpha_reg_fraction = config.get("alpha_reg_fraction", 1 / 8)
+        if self.alpha_reg_reduction not in ("ray", "slice"):
+            raise ValueError(f"Unknown reduction for alpha regularization: {self.alpha_reg_reduction}")
+        if self.criterion_str != "l1+ssim":
+            raise NotImplementedError(f'criterion "{self.criterion_str}": the fused loss implements "l1+ssim" (every shipped config)')
+        if use_automasking or self.median_thresholding or self.invalid_policy == "weight_guided_diverse":
+            raise NotImplementedError("automasking / median thresholding / weight_guided_diverse are not implemented")
+
+    @staticmethod
+    def get_loss_metric_names():
+        return ["loss", "loss_rgb_coarse", "loss_rgb_fine", "loss_ray_entropy", "loss_depth_reg"]
+
+    def _invalid(self, part):
+        """-> (invalid_ray (n,pc,h,w) float or None, invalid_mass or None): loss.py:101-121."""
+        if self.invalid_policy == "weight_guided" and "invalid_mass" in part:
+            return None, part["invalid_mass"]
+        inv = part["invalid"]
+        if self.invalid_policy == "strict":
+            ray = (inv > .5).any(-2).all(-1)
+        elif self.invalid_policy == "weight_guided":
+            ray = ((inv.to(torch.float32) * part["weights"].unsqueeze(-1)).sum(-2) > .9).all(-1)
+        else:
+            ray = torch.zeros(inv.shape[:-2], dtype=torch.bool, device=inv.device)
+        return ray.to(torch.float32), None
+
+    def __call__(self, data):
+        with torch.autograd.profiler.record_function("loss_computation"):
+            n_scales = len(data["coarse"])
+            coarse_0 = data["coarse"][0]
+            inv_ray, inv_mass = self._invalid(coarse_0)
+            mask = dict(invalid_ray=inv_ray, invalid_mass=inv_mass) if self.ignore_invalid else {}
+            keep = None                                   # (n,pc,h,w) 1 - invalid, for the torch-side regularisers
+            if self.ignore_invalid:
+                keep = 1 - (inv_ray if inv_ray is not None else (inv_mass > .9).all(-1).to(torch.float32))
+            rgb_gt = data["rgb_gt"]
+            zero = torch.zeros((), device=rgb_gt.device)
+            loss = zero
+            sums = {k: zero for k in ("coarse", "fine", "depth_reg", "alpha_reg", "surf", "eas", "depth_smooth")}
+            for scale in range(n_scales):
+                coarse, fine = data["coarse"][scale], data["fine"][scale]
+                rgb_loss = patch_photometric_loss(coarse["rgb"], rgb_gt, **mask)[0]                       # :151-167
+                sums["coarse"] = sums["coarse"] + rgb_loss.detach() * self.lambda_coarse
+                if len(fine) > 0:                                                                         # :170-186
+                    if fine["rgb"] is coarse["rgb"]:
+                        fine_loss = rgb_loss
+                    else:
+                        fmask = {}
+                        if self.ignore_invalid:
+                            fr, fm = self._invalid(data["fine"][0])
+                            fmask = dict(invalid_ray=fr, invalid_mass=fm)
+                        fine_loss = patch_photometric_loss(fine["rgb"], rgb_gt, **fmask)[0]
+                    sums["fine"] = sums["fine"] + fine_loss.detach() * self.lambda_fine
+                    rgb_loss = rgb_loss * self.lambda_coarse + fine_loss * self.lambda_fine
+                loss = loss + rgb_loss
+                depths = coarse["depth"]
+                if self.lambda_depth_reg > 0:                                                             # :192-198
+                    reg = (depths[:, :, 1:, :] - depths[:, :, :-1, :]).square().mean() + \
+                          (depths[:, :, :, 1:] - depths[:, :, :, :-1]).square().mean()
+                    sums["depth_reg"] = sums["depth_reg"] + reg.detach()
+                    loss = loss + reg * self.lambda_depth_reg
+                if self.lambda_alpha_reg > 0:                                                             # :200-230
+                    alphas = coarse["alphas"]
+                    alpha_sum = alphas[..., :-1].sum(-1)
+                    cap = torch.full_like(alpha_sum, alphas.shape[-1] * self.alpha_reg_fraction)
+                    if keep is not None:
+                        alpha_sum, cap = alpha_sum * keep, cap * keep
+                    if self.alpha_reg_reduction == "ray":
+                        reg = (alpha_sum - cap).clamp_min(0)
+                    else:
+                        reg = (alpha_sum.sum(-1) - cap.sum(-1)).clamp_min(0) / alpha_sum.shape[-1]
+                    reg = reg.mean()
+                    sums["alpha_reg"] = sums["alpha_reg"] + reg.detach()
+                    loss = loss + reg * self.lambda_alpha_reg
+                if self.lambda_surfaceness_reg > 0:                                                       # :232-245
+                    alphas = coarse["alphas"]
+                    sp = -torch.log(torch.exp(-alphas.abs()) + torch.exp(-(1 - alphas).abs())).mean(-1)
+                    if keep is not None:
+                        sp = sp * keep
+                    reg = sp.mean()
+                    sums["surf"] = sums["surf"] + reg.detach()
+                    loss = loss + reg * self.lambda_surfaceness_reg
+                if self.lambda_edge_aware_smoothness > 0:                                                 # :247-259
+                    eas = patch_edge_aware_smoothness(depths, rgb_gt, **mask)[0]
+                    sums["eas"] = sums["eas"] + eas.detach()
+                    loss = loss + eas * (self.lambda_edge_aware_smoothness / (2 ** scale))
+                if self.lambda_depth_smoothness > 0:                                                      # :261-266
+                    reg = (depths[..., :-1, :] - depths[..., 1:, :]).square().mean() + \
+                          (depths[..., :, :-1] - depths[..., :, 1:]).square().mean()
+                    sums["depth_smooth"] = sums["depth_smooth"] + reg.detach()
+                    loss = loss + reg * self.lambda_depth_smoothness
+            loss = loss / n_scales                                                                        # :269
+            entropy = zero
+            if self.lambda_entropy > 0:                                                                   # :271-281
+                import math
+                alphas = coarse_0["alphas"] + 1e-5
+                dens = alphas / alphas.sum(-1, keepdim=True)
+                ent = -(dens * torch.log(dens)).sum(-1) / math.log2(alphas.shape[-1])
+                ent = ent * (keep if keep is not None else 1.0)      # the reference masks unconditionally (:278)
+                entropy = ent.mean()
+                loss = loss + entropy * self.lambda_entropy
+            invalid_ratio = (1 - keep).mean() if keep is not None else zero
+        # one device->host transfer for all the logged scalars (the reference calls .item() nine times)
+        vals = torch.stack([sums["coarse"], sums["fine"], entropy.detach(), sums["depth_reg"], sums["alpha_reg"], sums["eas"],
+                            sums["depth_smooth"], invalid_ratio, loss.detach()]).tolist()
+        names = ["loss_rgb_coarse", "loss_rgb_fine", "loss_ray_entropy", "loss_depth_reg", "loss_alpha_reg", "loss_eas",
+                 "loss_depth_smoothness", "loss_invalid_ratio", "loss"]
+        return loss, dict(zip(names, vals))

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BTS_ABI_VERSION 7
+#define BTS_ABI_VERSION 8
 #define BTS_MAX_BLOCKS 8   /* ResnetFC blocks supported by the kernels */
 
 typedef struct CUstream_st* bts_stream_t; /* == cudaStream_t */
@@ -222,6 +222,17 @@ int bts_patch_loss_fwd(const float* pred, const float* gt, const float* invalid_
 int bts_patch_loss_bwd(const float* pred, const float* gt, const float* invalid_ray_or_null,
                        const float* invalid_mass_or_null, float mass_thresh, int64_t P, int32_t h, int32_t w, int32_t nv,
                        int32_t c, const int32_t* argmin, const float* g_per_ray, float* d_pred, bts_stream_t stream);
+
+/* Edge-aware smoothness of the rendered depth: replaces edge_aware_smoothness (models/bts/model/loss.py:21-40) and its
+ * invalid-ray mask (loss.py:247-256).  depth (P, h, w) ray distances, gt (P, h, w, c) the target colours of the same rays,
+ * masks as in bts_patch_loss_fwd (nv = number of views in invalid_mass).  per_ray (P, h, w): its mean is loss_eas.
+ * The backward writes d_depth (P, h, w) from the upstream gradient g_per_ray (P, h, w). */
+int bts_patch_smooth_fwd(const float* depth, const float* gt, const float* invalid_ray_or_null,
+                         const float* invalid_mass_or_null, float mass_thresh, int64_t P, int32_t h, int32_t w, int32_t nv,
+                         int32_t c, float* per_ray, bts_stream_t stream);
+int bts_patch_smooth_bwd(const float* depth, const float* gt, const float* invalid_ray_or_null,
+                         const float* invalid_mass_or_null, float mass_thresh, int64_t P, int32_t h, int32_t w, int32_t nv,
+                         int32_t c, const float* g_per_ray, float* d_depth, bts_stream_t stream);
 
 /* Name of the kernel family the last bts_render_fwd on this thread dispatched to ("general" | "tc"), for tests. */
 const char* bts_last_kernel(void);

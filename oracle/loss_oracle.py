@@ -46,3 +46,22 @@ def patch_loss(pred, gt, invalid_ray=None):
     if invalid_ray is not None:
         e = e * (1 - invalid_ray.to(torch.float32)).unsqueeze(-1)
     return e.mean(), e.squeeze(-1)
+
+
+def edge_aware_smoothness(gt, depth):
+    """gt (n,pc,h,w,3), depth (n,pc,h,w) -> (n,pc,h,w)   (loss.py:21-40; the F.interpolate there is the identity)."""
+    n, pc, h, w = depth.shape
+    img = gt.permute(0, 1, 4, 2, 3).reshape(-1, gt.shape[-1], h, w)
+    d = 1 / depth.reshape(-1, 1, h, w).clamp(1e-3, 80)
+    d = d / d.mean(dim=[2, 3], keepdim=True)
+    ex = (d[:, :, :, :-1] - d[:, :, :, 1:]).abs() * torch.exp(-(img[:, :, :, :-1] - img[:, :, :, 1:]).abs().mean(1, keepdim=True))
+    ey = (d[:, :, :-1, :] - d[:, :, 1:, :]).abs() * torch.exp(-(img[:, :, :-1, :] - img[:, :, 1:, :]).abs().mean(1, keepdim=True))
+    return (F.pad(ex, (0, 1)) + F.pad(ey, (0, 0, 0, 1))).view(n, pc, h, w)
+
+
+def smooth_loss(depth, gt, invalid_ray=None):
+    """Masked mean of loss.py:247-256 (the interpolate + ceil of the mask is the identity at equal sizes)."""
+    e = edge_aware_smoothness(gt, depth)
+    if invalid_ray is not None:
+        e = e * (1 - invalid_ray.to(torch.float32))
+    return e.mean(), e

@@ -189,6 +189,61 @@ def make_loss_golden(ref):
     print(f"loss_l1ssim: loss {loss.item():.6f} -> {os.path.getsize(path) / 1e3:.0f} kB")
 
 
+RECON_CONFIGS = {
+    "shipped": {"criterion": "l1+ssim", "invalid_policy": "weight_guided", "lambda_edge_aware_smoothness": 0.001},   # configs/exp_*.yaml
+    "all_terms": {"criterion": "l1+ssim", "invalid_policy": "strict", "lambda_fine": 0.5, "lambda_entropy": 0.1,
+                  "lambda_depth_reg": 0.01, "lambda_alpha_reg": 0.05, "lambda_surfaceness_reg": 0.02,
+                  "lambda_edge_aware_smoothness": 0.01, "lambda_depth_smoothness": 0.03, "alpha_reg_fraction": 0.25},
+    "unmasked_slice": {"criterion": "l1+ssim", "invalid_policy": "none", "lambda_alpha_reg": 0.05, "alpha_reg_reduction": "slice",
+                       "alpha_reg_fraction": 0.25, "lambda_edge_aware_smoothness": 0.002},
+}
+
+
+def recon_loss_inputs():
+    """Seeded stand-in for the trainer's ``data`` dict after PatchRaySampler.reconstruct (models/bts/trainer.py:236-258)."""
+    g = torch.Generator().manual_seed(123)
+    n, pc, h, w, nv, c, K = 2, 4, 8, 8, 2, 3, 8
+    gt = torch.rand((n, pc, h, w, c), generator=g)
+    rgb = (gt.unsqueeze(-2) + 0.1 * torch.randn((n, pc, h, w, nv, c), generator=g)).clamp(0, 1)
+    depth = 3 + 60 * torch.rand((n, pc, h, w), generator=g)
+    depth[0, 0, :2] = 90.0                                    # beyond the clamp of edge_aware_smoothness
+    depth[0, 1] = 20.0                                        # a flat patch: |d - d'| = 0 everywhere
+    alphas = torch.rand((n, pc, h, w, K), generator=g) * 0.5
+    weights = torch.softmax(torch.randn((n, pc, h, w, K), generator=g) * 2, -1)
+    invalid = torch.rand((n, pc, h, w, K, nv), generator=g) > 0.6
+    invalid[:, :, :3] = True                                  # rays whose whole mass is invalid in every view
+    invalid[:, :, 3:5, :, :, 1] = False
+    return dict(rgb=rgb, depth=depth, alphas=alphas, weights=weights, invalid=invalid.to(torch.float32), rgb_gt=gt)
+
+
+def make_recon_loss_golden(ref):
+    """ReconstructionLoss.__call__ of the unmodified reference (models/bts/model/loss.py:43-293) on the seeded data dict."""
+    import importlib
+    loss_mod = importlib.import_module("models.bts.model.loss")
+    out = {}
+    base = recon_loss_inputs()
+    for k, v in base.items():
+        out["in/" + k] = v.numpy()
+    for name, conf in RECON_CONFIGS.items():
+        t = {k: v.clone() for k, v in base.items()}
+        for k in ("rgb", "depth", "alphas"):
+            t[k].requires_grad_(True)
+        coarse = {k: t[k] for k in ("rgb", "depth", "alphas", "weights", "invalid")}
+        data = {"coarse": [coarse], "fine": [dict(coarse)], "rgb_gt": t["rgb_gt"]}      # trainer.py:246-247
+        loss, loss_dict = loss_mod.ReconstructionLoss(conf)(data)
+        loss.backward()
+        out[f"{name}/loss"] = loss.detach().numpy()
+        out[f"{name}/dict"] = np.frombuffer(json.dumps({k: float(v) for k, v in loss_dict.items()}).encode(), dtype=np.uint8)
+        for k in ("rgb", "depth", "alphas"):
+            out[f"{name}/grad_{k}"] = (t[k].grad if t[k].grad is not None else torch.zeros_like(t[k])).numpy()
+        print(f"recon_loss[{name}]: loss {loss.item():.6f} {loss_dict}")
+    os.makedirs(os.path.join(GOLDEN_DIR, "loss"), exist_ok=True)
+    path = os.path.join(GOLDEN_DIR, "loss", "reconstruction_loss.npz")
+    np.savez_compressed(path, **out)
+    print(f"-> {os.path.getsize(path) / 1e3:.0f} kB")
+
+
 if __name__ == "__main__":
     main()
     make_loss_golden(ref_import.load_reference())
+    make_recon_loss_golden(ref_import.load_reference())

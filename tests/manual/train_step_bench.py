@@ -23,6 +23,14 @@ rgb_gt = torch.rand((n, R, 3), generator=torch.Generator().manual_seed(9)).to(de
 def ours():
     net.zero_grad(set_to_none=True)
     net.encode(imgs, Ks, poses, ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
+    if LOSS == "shipped":       # the loss of every configs/exp_*.yaml through the drop-in ReconstructionLoss
+        from behindthescenes_b200.loss import ReconstructionLoss
+        out = wrapped(rays, u=u, want_weights=True, want_alphas=True, want_invalid=False, want_invalid_mass=True)["coarse"]
+        coarse = {"rgb": out["rgb"].view(n, R // 64, 8, 8, -1, 3), "depth": out["depth"].view(n, R // 64, 8, 8),
+                  "invalid_mass": out["invalid_mass"].view(n, R // 64, 8, 8, -1)}
+        crit = ReconstructionLoss({"criterion": "l1+ssim", "invalid_policy": "weight_guided", "lambda_edge_aware_smoothness": 0.001})
+        crit({"coarse": [coarse], "fine": [dict(coarse)], "rgb_gt": rgb_gt.view(n, R // 64, 8, 8, 3)})[0].backward()
+        return
     if LOSS == "l1ssim":
         from behindthescenes_b200.loss import patch_photometric_loss
         out = wrapped(rays, u=u, want_weights=True, want_alphas=True, want_invalid=False, want_invalid_mass=True)["coarse"]
@@ -63,6 +71,14 @@ def ref():
         t.grad = None
     st = orc.encode_state(imgs, Ks, poses, feats_g, wl.ids_encoder, wl.ids_render)
     out = orc.render(st, mlp_params(sdg), fcfg, rcfg, rays, u=u, empty_feature=sdg.get("empty_feature"), **wants)["coarse"]
+    if LOSS == "shipped":       # what ReconstructionLoss.__call__ runs for the shipped configs (fine = copy of coarse)
+        from oracle import loss_oracle as lo
+        inv = ((out["invalid"].to(torch.float32) * out["weights"].unsqueeze(-1)).sum(-2) > .9).all(-1).view(n, R // 64, 8, 8)
+        rgb6, gt5 = out["rgb"].view(n, R // 64, 8, 8, -1, 3), rgb_gt.view(n, R // 64, 8, 8, 3)
+        loss = lo.patch_loss(rgb6, gt5, inv)[0] + lo.patch_loss(rgb6, gt5, inv)[0] + \
+            0.001 * lo.smooth_loss(out["depth"].view(n, R // 64, 8, 8), gt5, inv)[0]
+        loss.backward()
+        return
     if LOSS == "l1ssim":
         from oracle import loss_oracle as lo
         inv = ((out["invalid"].to(torch.float32) * out["weights"].unsqueeze(-1)).sum(-2) > .9).all(-1)      # loss.py:107

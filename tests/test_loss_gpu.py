@@ -104,3 +104,81 @@ def test_errors_are_loud():
         patch_photometric_loss(torch.zeros(1, 1, 17, 8, 1, 3, device=dev), torch.zeros(1, 1, 17, 8, 3, device=dev))
     with pytest.raises(ValueError):
         patch_photometric_loss(torch.zeros(1, 100, 6, device=dev), torch.zeros(1, 100, 3, device=dev), patch=(8, 8))
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 8, 8), (1, 3, 5, 7), (2, 2, 16, 16), (1, 1, 1, 1)])
+def test_edge_aware_smoothness_against_oracle_autograd(shape):
+    from oracle import loss_oracle as lo
+    from behindthescenes_b200.loss import patch_edge_aware_smoothness
+    n, pc, h, w = shape
+    g = torch.Generator().manual_seed(sum(shape) + 1)
+    gt = torch.rand((n, pc, h, w, 3), generator=g)
+    depth = 2 + 90 * torch.rand(shape, generator=g)              # some beyond the 80 m clamp
+    depth[0, 0].fill_(7.0)                                       # a flat patch
+    invalid = torch.rand(shape, generator=g) > 0.7
+    ref = depth.clone().requires_grad_(True)
+    loss_o, per_ray_o = lo.smooth_loss(ref, gt, invalid)
+    loss_o.backward()
+    dev = torch.device("cuda")
+    d = depth.to(dev).requires_grad_(True)
+    loss, per_ray = patch_edge_aware_smoothness(d, gt.to(dev), invalid_ray=invalid.to(dev))
+    loss.backward()
+    assert (per_ray.detach().cpu() - per_ray_o.detach()).abs().max().item() < 1e-5 * max(1.0, per_ray_o.max().item())
+    assert abs(loss.item() - loss_o.item()) < 1e-5 * max(1.0, abs(loss_o.item()))
+    assert _rel(d.grad.cpu(), ref.grad) < GRAD_REL or ref.grad.abs().max() == 0
+
+
+@pytest.mark.parametrize("name", ["shipped", "all_terms", "unmasked_slice"])
+def test_reconstruction_loss_dropin_vs_reference_fixture(name):
+    """behindthescenes_b200.loss.ReconstructionLoss vs the unmodified reference class on the same data dict: loss,
+    every logged scalar, and the gradients that reach the renderer outputs."""
+    from oracle.make_goldens import RECON_CONFIGS
+    from tests.test_loss_oracle import load_recon_fixture
+    from behindthescenes_b200.loss import ReconstructionLoss
+    f = load_recon_fixture()
+    want = f["cfg"][name]
+    dev = torch.device("cuda")
+    t = {k: v.to(dev) for k, v in f["in"].items()}
+    for k in ("rgb", "depth", "alphas"):
+        t[k].requires_grad_(True)
+    coarse = {k: t[k] for k in ("rgb", "depth", "alphas", "weights", "invalid")}
+    data = {"coarse": [coarse], "fine": [dict(coarse)], "rgb_gt": t["rgb_gt"]}
+    crit = ReconstructionLoss(RECON_CONFIGS[name])
+    assert crit.get_loss_metric_names() == ["loss", "loss_rgb_coarse", "loss_rgb_fine", "loss_ray_entropy", "loss_depth_reg"]
+    loss, loss_dict = crit(data)
+    loss.backward()
+    assert abs(loss.item() - float(want["loss"])) < 2e-6 * max(1.0, abs(float(want["loss"])))
+    assert set(loss_dict) == set(want["dict"])
+    for k, v in want["dict"].items():
+        assert abs(loss_dict[k] - v) < 2e-6 * max(1.0, abs(v)), k
+    for k in ("rgb", "depth", "alphas"):
+        got = t[k].grad.cpu() if t[k].grad is not None else torch.zeros_like(f["in"][k])
+        ref = want["grad_" + k]
+        assert _rel(got, ref) < GRAD_REL or ref.abs().max() == 0, k
+
+
+def test_reconstruction_loss_accepts_invalid_mass_instead_of_flags():
+    """weight_guided with coarse["invalid_mass"] (the renderer's want_invalid_mass output) == with invalid + weights."""
+    from oracle.make_goldens import RECON_CONFIGS
+    from tests.test_loss_oracle import load_recon_fixture
+    from behindthescenes_b200.loss import ReconstructionLoss
+    f = load_recon_fixture()
+    dev = torch.device("cuda")
+    t = {k: v.to(dev) for k, v in f["in"].items()}
+    mass = (t["invalid"] * t["weights"].unsqueeze(-1)).sum(-2)
+    coarse = {"rgb": t["rgb"], "depth": t["depth"], "invalid_mass": mass}
+    loss, d = ReconstructionLoss(RECON_CONFIGS["shipped"])({"coarse": [coarse], "fine": [dict(coarse)], "rgb_gt": t["rgb_gt"]})
+    want = f["cfg"]["shipped"]
+    assert abs(loss.item() - float(want["loss"])) < 2e-6 and abs(d["loss_invalid_ratio"] - want["dict"]["loss_invalid_ratio"]) < 1e-7
+
+
+def test_reconstruction_loss_unsupported_options_raise():
+    from behindthescenes_b200.loss import ReconstructionLoss
+    for conf in ({"criterion": "l2"}, {"criterion": "l1+ssim", "median_thresholding": True},
+                 {"criterion": "l1+ssim", "invalid_policy": "weight_guided_diverse"}):
+        with pytest.raises(NotImplementedError):
+            ReconstructionLoss(conf)
+    with pytest.raises(NotImplementedError):
+        ReconstructionLoss({"criterion": "l1+ssim"}, use_automasking=True)
+    with pytest.raises(ValueError):
+        ReconstructionLoss({"criterion": "l1+ssim", "alpha_reg_reduction": "patch"})

@@ -33,3 +33,35 @@ def test_fixture_covers_the_edge_cases():
     assert (f["errors"][0, 0] == 0).all()                      # perfectly reconstructed patch: SSIM clamp at 0
     assert f["invalid"].any() and not f["invalid"].all()
     assert (f["per_ray"].squeeze(-1)[f["invalid"]] == 0).all()
+
+
+RECON_FIX = os.path.join(os.path.dirname(FIX), "reconstruction_loss.npz")
+
+
+def load_recon_fixture():
+    import json
+    z = np.load(RECON_FIX)
+    out = {"in": {}, "cfg": {}}
+    for k in z.files:
+        head, tail = k.split("/", 1)
+        if head == "in":
+            out["in"][tail] = torch.from_numpy(z[k])
+        else:
+            v = json.loads(bytes(z[k]).decode()) if tail == "dict" else torch.from_numpy(z[k])
+            out["cfg"].setdefault(head, {})[tail] = v
+    return out
+
+
+def test_smoothness_oracle_matches_reference_class_output():
+    """loss_eas and d loss / d depth of the reference's ReconstructionLoss (weight_guided mask and unmasked)."""
+    f = load_recon_fixture()
+    i = f["in"]
+    for name, lam, inv in (("shipped", 0.001, ((i["invalid"] * i["weights"].unsqueeze(-1)).sum(-2) > .9).all(-1)),
+                           ("unmasked_slice", 0.002, None)):
+        depth = i["depth"].clone().requires_grad_(True)
+        loss, _ = lo.smooth_loss(depth, i["rgb_gt"], inv)
+        assert abs(loss.item() - f["cfg"][name]["dict"]["loss_eas"]) < 1e-6
+        (loss * lam).backward()
+        assert torch.allclose(depth.grad, f["cfg"][name]["grad_depth"], atol=1e-9, rtol=1e-5)
+    # the fixture exercises the clamp and a flat patch
+    assert (f["cfg"]["unmasked_slice"]["grad_depth"][0, 0, :2] == 0).all()
