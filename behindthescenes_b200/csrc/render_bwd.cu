@@ -27,6 +27,46 @@ constexpr int kBwdMaxK = 256;
 
 // kBlock: one ResnetFC block (resnetfc.py:53-62) between lin_in and lin_out -- the RE10K configuration (d_hidden = 32,
 // NU = 1): h1 = h0 + fc1(relu(fc0(relu(h0)))); lane n owns hidden unit n and row n of the weight gradients.
+// This lane's NU consecutive hidden units of one row (one 8-byte access when NU == 2).
+template <int NU>
+__device__ __forceinline__ void load_units(const float* src, float (&dst)[NU]) {
+  if constexpr (NU == 2) {
+    const float2 v = *reinterpret_cast<const float2*>(src);
+    dst[0] = v.x; dst[1] = v.y;
+  } else {
+#pragma unroll
+    for (int n = 0; n < NU; ++n) dst[n] = src[n];
+  }
+}
+
+// Bilinear interpolation of the folded feature rows for this lane's units (or the g_empty row for invalid samples).
+template <int NU>
+__device__ __forceinline__ void gather_units(const KernelParams& p, const float4& a, const float4& w, int flags, int lane,
+                                             float (&out)[NU]) {
+  constexpr int Hd = NU * 32;
+#pragma unroll
+  for (int n = 0; n < NU; ++n) out[n] = 0.0f;
+  if (flags & 2) {
+#pragma unroll
+    for (int n = 0; n < NU; ++n) out[n] = __ldg(p.scene.g_empty + lane * NU + n);
+  } else if (flags & 1) {
+    const float* g00 = p.scene.G + (size_t)__float_as_int(a.x) * Hd + lane * NU;
+    const float* g10 = g00 + (size_t)__float_as_int(a.z) * Hd;
+    const size_t dxo = (size_t)__float_as_int(a.y) * Hd;
+    const float w00 = w.x * w.z, w01 = w.y * w.z, w10 = w.x * w.w, w11 = w.y * w.w;
+    if constexpr (NU == 2) {
+      const float2 v00 = __ldg(reinterpret_cast<const float2*>(g00)), v01 = __ldg(reinterpret_cast<const float2*>(g00 + dxo));
+      const float2 v10 = __ldg(reinterpret_cast<const float2*>(g10)), v11 = __ldg(reinterpret_cast<const float2*>(g10 + dxo));
+      out[0] = fmaf(v11.x, w11, fmaf(v10.x, w10, fmaf(v01.x, w01, v00.x * w00)));
+      out[1] = fmaf(v11.y, w11, fmaf(v10.y, w10, fmaf(v01.y, w01, v00.y * w00)));
+    } else {
+#pragma unroll
+      for (int n = 0; n < NU; ++n)
+        out[n] = fmaf(__ldg(g10 + dxo + n), w11, fmaf(__ldg(g10 + n), w10, fmaf(__ldg(g00 + dxo + n), w01, __ldg(g00 + n) * w00)));
+    }
+  }
+}
+
 template <int NU, bool kBlock>
 __global__ void __launch_bounds__(kBwdWarps * 32, kBlock ? 2 : 3) render_bwd_kernel(const BwdParams bp) {
   static_assert(!kBlock || NU == 1, "block backward is implemented for d_hidden = 32");
@@ -145,23 +185,11 @@ __global__ void __launch_bounds__(kBwdWarps * 32, kBlock ? 2 : 3) render_bwd_ker
             const float4 a = reinterpret_cast<const float4*>(w_taps)[(s0 + ss) * 2 + 0];
             const float4 w = reinterpret_cast<const float4*>(w_taps)[(s0 + ss) * 2 + 1];
             const int flags = __float_as_int(a.w);
-#pragma unroll
-            for (int n = 0; n < NU; ++n) {
-              float g = 0.0f;
-              if (flags & 2) g = __ldg(p.scene.g_empty + lane * NU + n);
-              else if (flags & 1) {
-                const float* g00 = p.scene.G + (size_t)__float_as_int(a.x) * Hd + lane * NU + n;
-                const float* g10 = g00 + (size_t)__float_as_int(a.z) * Hd;
-                const size_t dxo = (size_t)__float_as_int(a.y) * Hd;
-                g = fmaf(__ldg(g10 + dxo), w.y * w.w, fmaf(__ldg(g10), w.x * w.w, fmaf(__ldg(g00 + dxo), w.y * w.z, __ldg(g00) * (w.x * w.z))));
-              }
-              acc[ss][n] = g;
-            }
+            gather_units<NU>(p, a, w, flags, lane, acc[ss]);
           }
           for (int j = 0; j < P; ++j) {
             float wv[NU];
-#pragma unroll
-            for (int n = 0; n < NU; ++n) wv[n] = s_wpe[j * Hd + lane * NU + n];
+            load_units<NU>(s_wpe + j * Hd + lane * NU, wv);
             const float4 c0v = *reinterpret_cast<const float4*>(w_pe + j * 32 + s0);
             const float4 c1v = *reinterpret_cast<const float4*>(w_pe + j * 32 + s0 + 4);
             const float cv[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
@@ -260,6 +288,9 @@ __global__ void __launch_bounds__(kBwdWarps * 32, kBlock ? 2 : 3) render_bwd_ker
       const bool valid = k < K;
       const float z = z_ahead;
       z_ahead = (k + 32 < K) ? sample_depth(p, ray, k + 32, near_, far_) : 0.0f;
+      // samples whose dL/dlogit is exactly zero (rays the loss masked out, the capped last sample, ...) contribute to no
+      // gradient: skip whole chunks / 8-sample blocks of them (bit-identical result)
+      if (__ballot_sync(0xffffffffu, valid && sc_lbar[k] != 0.0f) == 0u) continue;
       const float X = __fadd_rn(ro0, __fmul_rn(z, rd0)), Y = __fadd_rn(ro1, __fmul_rn(z, rd1)), Z = __fadd_rn(ro2, __fmul_rn(z, rd2));
       const Proj pf = project(vf, X, Y, Z);
       {
@@ -278,29 +309,23 @@ __global__ void __launch_bounds__(kBwdWarps * 32, kBlock ? 2 : 3) render_bwd_ker
       __syncwarp();
       const int n_valid = min(32, K - c0);
       for (int s0 = 0; s0 < n_valid; s0 += 8) {
+        {
+          bool any = false;
+#pragma unroll
+          for (int ss = 0; ss < 8; ++ss) any |= (c0 + s0 + ss < K) && sc_lbar[c0 + s0 + ss] != 0.0f;
+          if (!any) continue;
+        }
         float acc[8][NU];
 #pragma unroll
         for (int ss = 0; ss < 8; ++ss) {
           const float4 a = reinterpret_cast<const float4*>(w_taps)[(s0 + ss) * 2 + 0];
           const float4 w = reinterpret_cast<const float4*>(w_taps)[(s0 + ss) * 2 + 1];
           const int flags = __float_as_int(a.w);
-#pragma unroll
-          for (int n = 0; n < NU; ++n) {
-            float g = 0.0f;
-            if (flags & 2) g = __ldg(p.scene.g_empty + lane * NU + n);
-            else if (flags & 1) {
-              const float* g00 = p.scene.G + (size_t)__float_as_int(a.x) * Hd + lane * NU + n;
-              const float* g10 = g00 + (size_t)__float_as_int(a.z) * Hd;
-              const size_t dxo = (size_t)__float_as_int(a.y) * Hd;
-              g = fmaf(__ldg(g10 + dxo), w.y * w.w, fmaf(__ldg(g10), w.x * w.w, fmaf(__ldg(g00 + dxo), w.y * w.z, __ldg(g00) * (w.x * w.z))));
-            }
-            acc[ss][n] = g;
-          }
+          gather_units<NU>(p, a, w, flags, lane, acc[ss]);
         }
         for (int j = 0; j < P; ++j) {
           float wv[NU];
-#pragma unroll
-          for (int n = 0; n < NU; ++n) wv[n] = s_wpe[j * Hd + lane * NU + n];
+          load_units<NU>(s_wpe + j * Hd + lane * NU, wv);
           const float4 c0v = *reinterpret_cast<const float4*>(w_pe + j * 32 + s0);
           const float4 c1v = *reinterpret_cast<const float4*>(w_pe + j * 32 + s0 + 4);
           const float cv[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};

@@ -18,7 +18,16 @@ def probe_loss(coarse):
     return total
 
 
-def oracle_gradients(wl, sd):
+def masked_probe_loss(coarse):
+    """probe_loss with two thirds of the rays masked out (zero upstream gradient on every output of those rays), the
+    situation the invalid-ray mask of the training loss creates (loss.py:160-161)."""
+    R = coarse["depth"].shape[1]
+    keep = (torch.arange(R, device=coarse["depth"].device) % 3 == 0).to(torch.float32).view(1, R)
+    masked = {k: coarse[k] * keep.view((1, R) + (1,) * (coarse[k].dim() - 2)) for k in ("rgb", "depth", "weights", "alphas")}
+    return probe_loss(masked)
+
+
+def oracle_gradients(wl, sd, loss_fn=probe_loss):
     """torch autograd through the oracle port (CPU)."""
     sd = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and not k.startswith("code_xyz")}
     feats = wl.feats.clone().requires_grad_(True)
@@ -27,7 +36,7 @@ def oracle_gradients(wl, sd):
     rcfg = orc.RenderConfig.from_renderer_conf(wl.renderer_conf)
     out = orc.render(st, mlp_params(sd), fcfg, rcfg, wl.rays, u=wl.u, empty_feature=sd.get("empty_feature"),
                      want_weights=True, want_alphas=True)["coarse"]
-    probe_loss(out).backward()
+    loss_fn(out).backward()
     g = {k: sd[k].grad for k in sd if k != "feats" and sd[k].grad is not None}
     g["feats"] = feats.grad
     return g

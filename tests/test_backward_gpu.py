@@ -13,14 +13,14 @@ pytestmark = pytest.mark.gpu
 GRAD_REL_TOL = 2e-3
 
 
-def cuda_gradients(wl, sd, precision=0, use_u=True):
+def cuda_gradients(wl, sd, precision=0, use_u=True, loss_fn=gu.probe_loss):
     net, wrapped = syn.build_model(wl, "cuda", state_dict=sd)
     wrapped.renderer.precision = precision
     net.encoder.feats.requires_grad_(True)
     net.encode(wl.images.cuda(), wl.Ks.cuda(), wl.poses_c2w.cuda(), ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
     out = wrapped(wl.rays.cuda(), want_weights=True, want_alphas=True, u=wl.u.cuda() if use_u else None)["coarse"]
     assert out["rgb"].requires_grad and out["depth"].requires_grad and not out["invalid"].requires_grad
-    gu.probe_loss(out).backward()
+    loss_fn(out).backward()
     g = {"mlp_coarse.lin_in.weight": net.mlp_coarse.lin_in.weight.grad, "mlp_coarse.lin_in.bias": net.mlp_coarse.lin_in.bias.grad,
          "mlp_coarse.lin_out.weight": net.mlp_coarse.lin_out.weight.grad, "mlp_coarse.lin_out.bias": net.mlp_coarse.lin_out.bias.grad,
          "feats": net.encoder.feats.grad}
@@ -131,4 +131,17 @@ def test_backward_option_coverage_vs_oracle_autograd(variant):
     ref = gu.oracle_gradients(wl, sd)
     errs = {k: gu.rel_err(got[k], ref[k]) for k in ref}
     print(variant, errs)
+    assert max(errs.values()) <= GRAD_REL_TOL, errs
+
+
+def test_backward_with_masked_rays_vs_oracle_autograd():
+    """Rays with an all-zero upstream gradient (the loss's invalid mask): the backward skips their sample blocks; the
+    gradients must equal autograd's."""
+    wl = syn.cfg3_kitti_raw_train(H=48, W=160, n=2, lin_out_bias=-4.0, seed=43, ray_subsample=1024)
+    cpu_net, _ = syn.build_model(wl, "cpu")
+    sd = {k: v.clone() for k, v in cpu_net.state_dict().items() if not k.startswith("encoder.")}
+    got, _ = cuda_gradients(wl, sd, loss_fn=gu.masked_probe_loss)
+    ref = gu.oracle_gradients(wl, sd, loss_fn=gu.masked_probe_loss)
+    errs = {k: gu.rel_err(got[k], ref[k]) for k in ref}
+    print(errs)
     assert max(errs.values()) <= GRAD_REL_TOL, errs

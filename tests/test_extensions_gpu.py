@@ -69,8 +69,18 @@ def test_in_kernel_ray_generation_matches_ray_tensor_path(precision):
     assert torch.allclose(b["depth_z"].cpu(), b["depth"].cpu() * fac, rtol=2e-6, atol=1e-6)
 
 
-def test_extensions_are_inference_only():
+def test_output_diet_trains_but_in_kernel_rays_are_inference_only():
+    """want_invalid=False / want_invalid_mass=True are part of the autograd node (non-differentiable outputs, as in the
+    reference where loss.py:105-108 only thresholds them); in-kernel ray generation / depth_z stay inference-only."""
     wl = syn.cfg2_kitti360_eval(H=16, W=48, ray_subsample=64)
     net, wrapped = _model(wl)
+    out = wrapped(wl.rays.cuda(), u=wl.u.cuda(), want_weights=True, want_invalid=False, want_invalid_mass=True)["coarse"]
+    assert "invalid" not in out and out["rgb"].requires_grad and not out["invalid_mass"].requires_grad
+    with torch.no_grad():
+        ref = wrapped(wl.rays.cuda(), u=wl.u.cuda(), want_weights=True)["coarse"]
+    mass = (ref["invalid"] * ref["weights"].unsqueeze(-1)).sum(-2)
+    assert torch.allclose(out["invalid_mass"], mass, atol=1e-5) and torch.equal(out["rgb"].detach(), ref["rgb"])
+    out["rgb"].sum().backward()
+    assert net.mlp_coarse.lin_in.weight.grad is not None
     with pytest.raises(NotImplementedError):
-        wrapped(wl.rays.cuda(), want_invalid_mass=True)              # grad enabled + trainable parameters
+        wrapped.render_views(wl.poses_c2w.cuda()[:, :1], wl.Ks.cuda()[:, :1], 16, 48, 3.0, 80.0)   # grad enabled + trainable parameters
