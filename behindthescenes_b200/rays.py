@@ -5,7 +5,7 @@ loss / metric numerators -- the reference's ``sync_all_reduce("_num_examples:SUM
 (``utils/metrics.py:31``).  This replaces the reference's dormant single-process ``DataParallel(dim=1)`` over rays
 (``models/common/render/nerf.py:453-457``).
 """
-from typing import Dict, Tuple
+from typing import Dict, Iterable, Tuple
 
 import torch
 import torch.distributed as dist
@@ -38,6 +38,39 @@ def allreduce_sums(values: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     buf = torch.stack([values[k].detach().to(torch.float64).reshape(()) for k in keys])
     dist.all_reduce(buf, op=dist.ReduceOp.SUM)
     return {k: buf[i].to(values[k].dtype) for i, k in enumerate(keys)}
+
+
+def allreduce_gradients(parameters: Iterable[torch.Tensor], n_local_rays: int) -> int:
+    """Training under a ray shard (BASELINE config 3): every rank back-propagated the MEAN loss of its own rays; turn the
+    local gradients into the gradient of the mean over ALL rays with ONE packed all-reduce (NCCL over NVLink; gloo in the
+    CPU tests): g = sum_r (n_r / n_total) g_r.  Parameters without a gradient on some rank contribute zeros.  Returns the
+    global ray count.  This is the per-process form of what ``DataParallel(dim=1)`` (``nerf.py:453-457``) would have
+    summed on device 0; the reference trains single-GPU (``utils/base_trainer.py:297``)."""
+    params = [p for p in parameters if p.requires_grad]
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1 or not params:
+        return int(n_local_rays)
+    dev = params[0].device
+    sizes = [p.numel() for p in params]
+    flat = torch.zeros(sum(sizes) + 1, device=dev, dtype=torch.float32)
+    off = 0
+    for p, n in zip(params, sizes):
+        if p.grad is not None:
+            flat[off:off + n] = p.grad.reshape(-1).to(torch.float32)
+        off += n
+    flat[:-1] *= float(n_local_rays)
+    flat[-1] = float(n_local_rays)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    n_total = flat[-1].clone()
+    flat[:-1] /= n_total
+    off = 0
+    for p, n in zip(params, sizes):
+        g = flat[off:off + n].view_as(p).to(p.dtype)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        off += n
+    return int(round(n_total.item()))
 
 
 def gather_ray_outputs(local: torch.Tensor, n_rays: int, granularity: int = 1) -> torch.Tensor:

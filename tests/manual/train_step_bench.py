@@ -9,7 +9,13 @@ from tests import grad_util as gu
 n, R = 16, 2048                       # configs/exp_kitti_raw.yaml: batch_size 16, ray_batch_size 2048, patch 8x8
 H, W = 192, 640
 wl = syn.cfg3_kitti_raw_train(H=H, W=W, n=n, lin_out_bias=-4.0, seed=61, ray_subsample=R)
-dev = torch.device("cuda")
+WORLD, RANK = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0))
+dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+torch.cuda.set_device(dev)
+if WORLD > 1:      # ray shard, weak scaling: every rank renders its own 16 x 2048 patch rays of the replicated frames
+    import torch.distributed as dist
+    from behindthescenes_b200 import rays as R_
+    dist.init_process_group("nccl", device_id=dev)
 cpu_net, _ = syn.build_model(wl, "cpu")
 sd = {k: v.clone() for k, v in cpu_net.state_dict().items() if not k.startswith("encoder.")}
 net, wrapped = syn.build_model(wl, dev, state_dict=sd)
@@ -30,6 +36,8 @@ def ours():
                   "invalid_mass": out["invalid_mass"].view(n, R // 64, 8, 8, -1)}
         crit = ReconstructionLoss({"criterion": "l1+ssim", "invalid_policy": "weight_guided", "lambda_edge_aware_smoothness": 0.001})
         crit({"coarse": [coarse], "fine": [dict(coarse)], "rgb_gt": rgb_gt.view(n, R // 64, 8, 8, 3)})[0].backward()
+        if WORLD > 1:      # one packed NCCL all-reduce of the field's gradients (the encoder's would ride in the same bucket)
+            R_.allreduce_gradients(net.mlp_coarse.parameters(), n * R)
         return
     if LOSS == "l1ssim":
         from behindthescenes_b200.loss import patch_photometric_loss
@@ -44,6 +52,8 @@ def timeit(fn, steps=10, warm=3):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    if WORLD > 1:
+        dist.barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(steps):
@@ -54,6 +64,16 @@ def timeit(fn, steps=10, warm=3):
 
 
 ms_ours = timeit(ours, steps=int(os.environ.get("STEPS", 10)), warm=int(os.environ.get("WARM", 3)))
+if WORLD > 1:
+    t = torch.tensor([ms_ours], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if RANK == 0:
+        print(json.dumps({"workload": f"cfg3-shaped training step, ray shard x{WORLD} (weak: {n}x{R} rays per rank), loss={LOSS}, "
+                                      "gradient all-reduce over NCCL every step", "n_gpus": WORLD, "ms_per_step_max_over_ranks": t.item(),
+                          "rays_per_s": WORLD * n * R / t.item() * 1e3}))
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0)
 if os.environ.get("ONLY_OURS"):          # launch-list runs under ncu
     print(json.dumps({"ms_ours": ms_ours, "loss": LOSS}))
     sys.exit(0)

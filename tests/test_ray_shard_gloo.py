@@ -60,3 +60,44 @@ def test_two_rank_shard_allreduce_gather():
     assert res[0][4] == (2, 51, 8) and res[1][4] == (2, 50, 8)
     for _, s, c, ok, _ in res:
         assert abs(s - want) < 1e-3 and c == 202.0 and ok
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        lin = torch.nn.Linear(8, 3)
+        unused = torch.nn.Parameter(torch.zeros(2))                 # a parameter only rank 0 touches
+        g = torch.Generator().manual_seed(0)
+        rays = torch.rand((2, 101, 8), generator=g)
+        mine = R.shard_rays(rays, rank, world)                       # uneven blocks: 51 / 50 rays
+        loss = lin(mine).square().mean() + (unused.sum() if rank == 0 else 0.0)
+        loss.backward()
+        n_total = R.allreduce_gradients([lin.weight, lin.bias, unused], mine.shape[0] * mine.shape[1])
+        q.put((rank, n_total, lin.weight.grad.clone(), lin.bias.grad.clone(), unused.grad.clone()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_equals_full_batch_gradient():
+    """Sharded mean-loss gradients, ray-count weighted and all-reduced in one packed collective, equal the gradient of the
+    mean over all rays (uneven shards, a parameter without gradient on one rank)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(8, 3)
+    rays = torch.rand((2, 101, 8), generator=torch.Generator().manual_seed(0))
+    lin(rays).square().mean().backward()
+    for _, n_total, gw, gb, gu_ in res:
+        assert n_total == 202
+        assert torch.allclose(gw, lin.weight.grad, atol=1e-6) and torch.allclose(gb, lin.bias.grad, atol=1e-6)
+        assert torch.allclose(gu_, torch.full((2,), 102 / 202), atol=1e-6)      # rank 0's share of the ray count
