@@ -10,7 +10,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libbts_b200.so")
 
 BTS_MAX_BLOCKS = 8
-ABI_VERSION = 8
+ABI_VERSION = 9
 _fp = C.POINTER(C.c_float)
 
 
@@ -63,6 +63,7 @@ EXPORTS = {
     "bts_abi_version": (C.c_int, []),
     "bts_last_error": (C.c_char_p, []),
     "bts_last_kernel": (C.c_char_p, []),
+    "bts_last_bwd_kernel": (C.c_char_p, []),
     "bts_debug_tc_timeouts": (C.c_int, []),
     "bts_fold_features": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

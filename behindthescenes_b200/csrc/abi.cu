@@ -12,7 +12,8 @@ cudaError_t launch_general(const KernelParams& p, bool points, cudaStream_t stre
 size_t general_smem_bytes(int Hd, int p_pad, int n_blocks);
 cudaError_t launch_fold(const float* feat, int n, int C, int H, int W, const float* w_in, int ld, const float* b_in, int Hd,
                         const float* empty, float* G, float* g_empty, cudaStream_t stream);
-cudaError_t launch_bwd(const BwdParams& bp, cudaStream_t stream);
+cudaError_t launch_bwd(const BwdParams& bp, cudaStream_t stream, bool* used_tc);
+int bwd_tc_barrier_timeouts();
 size_t bwd_smem_bytes(int Hd, int p_pad, int K, int n_blocks);
 bool tc_supported(const KernelParams& p);
 cudaError_t launch_tc(const KernelParams& p, bool points, cudaStream_t stream);
@@ -31,6 +32,7 @@ cudaError_t launch_pack_images(const float* img, int nv_total, int Cc, int Hc, i
 namespace {
 thread_local char g_err[512] = "";
 thread_local const char* g_kernel = "none";
+const char* volatile g_bwd_kernel = "none";   // process-wide: autograd runs the backward on its own thread
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -68,7 +70,8 @@ extern "C" {
 int bts_abi_version(void) { return BTS_ABI_VERSION; }
 const char* bts_last_error(void) { return g_err; }
 const char* bts_last_kernel(void) { return g_kernel; }
-int bts_debug_tc_timeouts(void) { return bts::tc_barrier_timeouts() + bts::fold_barrier_timeouts() + bts::fold_bwd_barrier_timeouts(); }
+const char* bts_last_bwd_kernel(void) { return g_bwd_kernel; }
+int bts_debug_tc_timeouts(void) { return bts::tc_barrier_timeouts() + bts::fold_barrier_timeouts() + bts::fold_bwd_barrier_timeouts() + bts::bwd_tc_barrier_timeouts(); }
 
 int bts_fold_features(const float* feat_nchw, int32_t n, int32_t C, int32_t H, int32_t W, const float* w_in,
                       int32_t ld_w_in, const float* b_in, int32_t Hd, const float* empty_feature_or_null, float* G_out,
@@ -165,7 +168,9 @@ int bts_render_bwd(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg*
   bp.d_G = grads->d_G; bp.d_g_empty = grads->d_g_empty; bp.d_w_pe = grads->d_w_pe; bp.d_w_out = grads->d_w_out;
   bp.d_b_out = grads->d_b_out;
   bp.d_fc0_w = grads->d_fc0_w; bp.d_fc0_b = grads->d_fc0_b; bp.d_fc1_w = grads->d_fc1_w; bp.d_fc1_b = grads->d_fc1_b;
-  const cudaError_t e = bts::launch_bwd(bp, reinterpret_cast<cudaStream_t>(stream));
+  bool used_tc = false;
+  const cudaError_t e = bts::launch_bwd(bp, reinterpret_cast<cudaStream_t>(stream), &used_tc);
+  g_bwd_kernel = used_tc ? "tc" : "general";
   if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_render_bwd: %s", cudaGetErrorString(e));
   return BTS_OK;
 }

@@ -16,6 +16,8 @@
 // Reference forward being differentiated: models/common/render/nerf.py:283-304 (alpha, cumprod, weights, rgb, depth),
 // models/bts/model/models_bts.py:138-216, :311-313 (features, softplus), resnetfc.py:132-184 (n_blocks = 0).
 // The reference gets these gradients from torch autograd; tests compare against autograd through the oracle.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "render_phases.cuh"
 #include "bwd_params.cuh"
@@ -483,7 +485,15 @@ static cudaError_t launch_bwd_t(const BwdParams& bp, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_bwd(const BwdParams& bp, cudaStream_t stream) {
+bool bwd_tc_supported(const BwdParams& bp);
+cudaError_t launch_bwd_tc(const BwdParams& bp, cudaStream_t stream);
+
+// *used_tc (optional) reports which kernel family ran.  BTS_BWD_SIMT=1 forces the CUDA-core kernel (tests compare the two).
+cudaError_t launch_bwd(const BwdParams& bp, cudaStream_t stream, bool* used_tc) {
+  const char* force_simt = getenv("BTS_BWD_SIMT");
+  const bool tc = !(force_simt && force_simt[0] == '1') && bwd_tc_supported(bp);
+  if (used_tc) *used_tc = tc;
+  if (tc) return launch_bwd_tc(bp, stream);
   if (bp.k.mlp.n_blocks == 1 && bp.k.mlp.Hd == 32) return launch_bwd_t<1, true>(bp, stream);
   if (bp.k.mlp.n_blocks != 0) return cudaErrorInvalidValue;
   switch (bp.k.mlp.Hd / 32) {

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BTS_ABI_VERSION 8
+#define BTS_ABI_VERSION 9
 #define BTS_MAX_BLOCKS 8   /* ResnetFC blocks supported by the kernels */
 
 typedef struct CUstream_st* bts_stream_t; /* == cudaStream_t */
@@ -236,6 +236,8 @@ int bts_patch_smooth_bwd(const float* depth, const float* gt, const float* inval
 
 /* Name of the kernel family the last bts_render_fwd on this thread dispatched to ("general" | "tc"), for tests. */
 const char* bts_last_kernel(void);
+/* Same for the last bts_render_bwd: "tc" (tensor-core backward: d_hidden 64, no blocks, saved sigma, K % 32 == 0) | "general". */
+const char* bts_last_bwd_kernel(void);
 
 /* Debug/test hook (synchronises): number of bounded mbarrier waits that expired inside the tensor-core kernel since
  * the library was loaded.  Always 0 unless the kernel has a pipeline bug. */

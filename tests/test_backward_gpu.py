@@ -145,3 +145,24 @@ def test_backward_with_masked_rays_vs_oracle_autograd():
     errs = {k: gu.rel_err(got[k], ref[k]) for k in ref}
     print(errs)
     assert max(errs.values()) <= GRAD_REL_TOL, errs
+
+
+def test_tensor_core_backward_matches_cuda_core_backward(monkeypatch):
+    """The tcgen05 backward (d_hidden 64, no blocks, saved sigma) and the CUDA-core backward on the same training batch:
+    same gradients up to accumulation order; both within tolerance of autograd through the oracle."""
+    from behindthescenes_b200 import _lib
+    lib = _lib.load()
+    wl = syn.cfg3_kitti_raw_train(H=48, W=160, n=2, lin_out_bias=-4.0, seed=47, ray_subsample=2048)
+    cpu_net, _ = syn.build_model(wl, "cpu")
+    sd = {k: v.clone() for k, v in cpu_net.state_dict().items() if not k.startswith("encoder.")}
+    got_tc, _ = cuda_gradients(wl, sd)
+    assert lib.bts_last_bwd_kernel() == b"tc" and lib.bts_debug_tc_timeouts() == 0
+    monkeypatch.setenv("BTS_BWD_SIMT", "1")
+    got_si, _ = cuda_gradients(wl, sd)
+    assert lib.bts_last_bwd_kernel() == b"general"
+    errs = {k: gu.rel_err(got_tc[k], got_si[k]) for k in got_si}
+    print(errs)
+    assert max(errs.values()) <= 1e-4, errs
+    ref = gu.oracle_gradients(wl, sd)
+    errs = {k: gu.rel_err(got_tc[k], ref[k]) for k in ref}
+    assert max(errs.values()) <= GRAD_REL_TOL, errs
