@@ -22,6 +22,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "render_phases.cuh"
 #include "bwd_params.cuh"
@@ -242,15 +244,25 @@ __global__ void __launch_bounds__(kThreads, 2) render_bwd_tc_kernel(const BwdPar
         sc_fac[k] = capped ? 0.0f : fabsf(delta) * e * (1.0f - expf(-sigma));
       }
       __syncwarp();
-      if (lane == 0) {       // reverse recurrence (division-free)
-        float Rj = 0.0f;
-        for (int j = K - 1; j >= 0; --j) {
-          const float a = sc_alpha[j], T = sc_T[j];
-          float abar = fmaf(sc_wbar[j], T, -T * Rj);
-          if (bp.g_alphas) abar += __ldg(bp.g_alphas + ray * K + j);
-          sc_lbar[j] = active ? abar * sc_fac[j] : 0.0f;
-          Rj = fmaf(sc_wbar[j], a, ((1.0f - a) + 1e-10f) * Rj);
+      // reverse recurrence R_{j-1} = wbar_j a_j + t_j R_j (division-free) as a suffix scan of the affine maps
+      // f_j(x) = b_j + t_j x over the lanes of a chunk, chunks visited last to first with the carry R_{c0+31}
+      float R_carry = 0.0f;   // R_{K-1} = 0
+      for (int c0 = K - 32; c0 >= 0; c0 -= 32) {
+        const int k = c0 + lane;
+        const float a = sc_alpha[k], Tk = sc_T[k], wb = sc_wbar[k];
+        float St = (1.0f - a) + 1e-10f, Sb = wb * a;               // S_l = f_l o f_{l+1} o ... o f_31 after the scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float t2 = __shfl_down_sync(0xffffffffu, St, o), b2 = __shfl_down_sync(0xffffffffu, Sb, o);
+          if (lane + o < 32) { Sb = fmaf(St, b2, Sb); St *= t2; }
         }
+        // R_j = S_{l+1}(R_carry); lane 31: the carry itself
+        const float nt = __shfl_down_sync(0xffffffffu, St, 1), nb = __shfl_down_sync(0xffffffffu, Sb, 1);
+        const float Rj = lane == 31 ? R_carry : fmaf(nt, R_carry, nb);
+        float abar = fmaf(wb, Tk, -Tk * Rj);
+        if (bp.g_alphas) abar += __ldg(bp.g_alphas + ray * K + k);
+        sc_lbar[k] = active ? abar * sc_fac[k] : 0.0f;
+        R_carry = fmaf(__shfl_sync(0xffffffffu, St, 0), R_carry, __shfl_sync(0xffffffffu, Sb, 0));   // R_{c0-1}
       }
       __syncwarp();
     }
@@ -406,45 +418,50 @@ __global__ void __launch_bounds__(kThreads, 2) render_bwd_tc_kernel(const BwdPar
         const float4* wrh = reinterpret_cast<const float4*>(smem + kOffWrawA);
         const float4* wrl = reinterpret_cast<const float4*>(smem + kOffWrawB);
         const __nv_bfloat16 one = __float2bfloat16_rn(1.0f), zero = __float2bfloat16_rn(0.0f);
+        auto epilogue = [&](auto raw_tag) {
+          constexpr bool kRaw = decltype(raw_tag)::value;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t dv[16];
-          tc::tmem_ld_x16(t_lane + kColD + c * 16, dv);
-          tc::tmem_ld_wait();
+          for (int c = 0; c < 4; ++c) {
+            uint32_t dv[16];
+            tc::tmem_ld_x16(t_lane + kColD + c * 16, dv);
+            tc::tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float4 g = grow[c * 4 + e];
-            const float4 wv = wo4[c * 4 + e];
-            const float gv[4] = {g.x, g.y, g.z, g.w}, wo[4] = {wv.x, wv.y, wv.z, wv.w};
-            float hb[4];
+            for (int e = 0; e < 4; ++e) {
+              const float4 g = grow[c * 4 + e];
+              const float4 wv = wo4[c * 4 + e];
+              const float gv[4] = {g.x, g.y, g.z, g.w}, wo[4] = {wv.x, wv.y, wv.z, wv.w};
+              float hb[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const int u = c * 16 + e * 4 + t;
-              float h = __uint_as_float(dv[e * 4 + t]) + gv[t];
-              if (big) {       // raw-coordinate part of lin_in in fp32 (as the forward)
-                const float4 wh = wrh[u], wl = wrl[u];
-                h = fmaf(wh.z + wl.z, pv[2], fmaf(wh.y + wl.y, pv[1], fmaf(wh.x + wl.x, pv[0], h)));
+              for (int t = 0; t < 4; ++t) {
+                const int u = c * 16 + e * 4 + t;
+                float h = __uint_as_float(dv[e * 4 + t]) + gv[t];
+                if (kRaw) {      // raw-coordinate part of lin_in in fp32 for far-outside samples (as the forward)
+                  const float4 wh = wrh[u], wl = wrl[u];
+                  if (big) h = fmaf(wh.z + wl.z, pv[2], fmaf(wh.y + wl.y, pv[1], fmaf(wh.x + wl.x, pv[0], h)));
+                }
+                const bool on = h > 0.0f;
+                acc_wout[u] = fmaf(lb, fmaxf(h, 0.0f), acc_wout[u]);
+                hb[t] = on ? lb * wo[t] : 0.0f;
+                *reinterpret_cast<__nv_bfloat16*>(mask_col + u * 16) = on ? one : zero;
               }
-              const bool on = h > 0.0f;
-              acc_wout[u] = fmaf(lb, fmaxf(h, 0.0f), acc_wout[u]);
-              hb[t] = on ? lb * wo[t] : 0.0f;
-              *reinterpret_cast<__nv_bfloat16*>(mask_col + u * 16) = on ? one : zero;
-            }
-            if (hb[0] != 0.0f || hb[1] != 0.0f || hb[2] != 0.0f || hb[3] != 0.0f) {
-              const int q = c * 4 + e;
-              if (is_empty) {
+              if (hb[0] != 0.0f || hb[1] != 0.0f || hb[2] != 0.0f || hb[3] != 0.0f) {
+                const int q = c * 4 + e;
+                if (is_empty) {
 #pragma unroll
-                for (int t = 0; t < 4; ++t)
-                  if (hb[t] != 0.0f) atomicAdd(bp.d_g_empty + q * 4 + t, hb[t]);
-              } else {
-                atomicAdd(d00 + q, make_float4(hb[0] * tw.x, hb[1] * tw.x, hb[2] * tw.x, hb[3] * tw.x));
-                atomicAdd(d00 + dxo + q, make_float4(hb[0] * tw.y, hb[1] * tw.y, hb[2] * tw.y, hb[3] * tw.y));
-                atomicAdd(d10 + q, make_float4(hb[0] * tw.z, hb[1] * tw.z, hb[2] * tw.z, hb[3] * tw.z));
-                atomicAdd(d10 + dxo + q, make_float4(hb[0] * tw.w, hb[1] * tw.w, hb[2] * tw.w, hb[3] * tw.w));
+                  for (int t = 0; t < 4; ++t)
+                    if (hb[t] != 0.0f) atomicAdd(bp.d_g_empty + q * 4 + t, hb[t]);
+                } else {
+                  atomicAdd(d00 + q, make_float4(hb[0] * tw.x, hb[1] * tw.x, hb[2] * tw.x, hb[3] * tw.x));
+                  atomicAdd(d00 + dxo + q, make_float4(hb[0] * tw.y, hb[1] * tw.y, hb[2] * tw.y, hb[3] * tw.y));
+                  atomicAdd(d10 + q, make_float4(hb[0] * tw.z, hb[1] * tw.z, hb[2] * tw.z, hb[3] * tw.z));
+                  atomicAdd(d10 + dxo + q, make_float4(hb[0] * tw.w, hb[1] * tw.w, hb[2] * tw.w, hb[3] * tw.w));
+                }
               }
             }
           }
-        }
+        };
+        if (__any_sync(0xffffffffu, big)) epilogue(std::true_type{});
+        else epilogue(std::false_type{});
       }
       tc::fence_proxy_async_smem();        // operand tiles (P1: lbar*code, P3: mask) -> async proxy
       tc::tc_fence_before_sync();
@@ -528,13 +545,12 @@ cudaError_t launch_bwd_tc(const BwdParams& bp, cudaStream_t stream) {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
-  int dev = 0, sms = 148, occ = 1;
+  int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, bwdtc::kThreads, smem);
-  if (e != cudaSuccess) return e;
-  if (occ < 1) return cudaErrorInvalidConfiguration;
-  if (occ > 2) occ = 2;                                  // 256 TMEM columns per CTA
+  // two CTAs per SM (256 TMEM columns each) when two footprints fit the 228 KB of an SM; the occupancy query would
+  // answer for the default carve-out, not the one requested above
+  const int occ = 2 * (smem + 1024) <= 233472 ? 2 : 1;
   const int64_t want = (bp.k.n_items + 3) / 4;
   const int64_t cap = (int64_t)sms * occ;
   const int grid = (int)(want < cap ? (want > 0 ? want : 1) : cap);
