@@ -27,6 +27,15 @@ def masked_probe_loss(coarse):
     return probe_loss(masked)
 
 
+def block_masked_probe_loss(coarse):
+    """probe_loss with runs of 8 consecutive rays masked out (16 of every 24): whole 4-ray passes of the tensor-core
+    backward see zero upstream gradients and take its skip path."""
+    R = coarse["depth"].shape[1]
+    keep = ((torch.arange(R, device=coarse["depth"].device) // 8) % 3 == 0).to(torch.float32).view(1, R)
+    masked = {k: coarse[k] * keep.view((1, R) + (1,) * (coarse[k].dim() - 2)) for k in ("rgb", "depth", "weights", "alphas")}
+    return probe_loss(masked)
+
+
 def oracle_gradients(wl, sd, loss_fn=probe_loss):
     """torch autograd through the oracle port (CPU)."""
     sd = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and not k.startswith("code_xyz")}

@@ -166,3 +166,35 @@ def test_tensor_core_backward_matches_cuda_core_backward(monkeypatch):
     ref = gu.oracle_gradients(wl, sd)
     errs = {k: gu.rel_err(got_tc[k], ref[k]) for k in ref}
     assert max(errs.values()) <= GRAD_REL_TOL, errs
+
+
+@pytest.mark.parametrize("variant", ["K128_two_views", "K96_ragged_passes_block_mask"])
+def test_tensor_core_backward_shapes_vs_oracle_autograd(variant):
+    """Shapes the tensor-core backward handles beyond the K=64 training batch: K=128 (one CTA per SM), K=96 (three chunks),
+    a ray count that is not a multiple of the 4 rays of a pass (idle warps in the last pass), whole passes with zero upstream
+    gradient (skip path), learn_empty rows."""
+    from behindthescenes_b200 import _lib
+    P = syn._pose
+    if variant == "K128_two_views":
+        mc = syn.kitti_model_conf(learn_empty=True)
+        rc = syn.kitti_renderer_conf(128)
+        wl = syn.make_workload("bw_k128", H=24, W=64, poses=[P(), P(tx=0.54)], model_conf=mc, renderer_conf=rc,
+                               ids_encoder=[0], ids_render=[0, 1], ray_poses=[P(tx=0.25, tz=-0.4, yaw_deg=10.0)],
+                               ray_subsample=512, seed=91, lin_out_bias=-3.0)
+        loss_fn = gu.probe_loss
+    else:
+        mc = syn.kitti_model_conf(learn_empty=False)
+        rc = syn.kitti_renderer_conf(96)
+        wl = syn.make_workload("bw_k96", H=24, W=64, poses=[P(), P(tx=0.54)], model_conf=mc, renderer_conf=rc,
+                               ids_encoder=[0], ids_render=[1], ray_poses=[P(tx=0.3, tz=0.2, yaw_deg=-15.0)],
+                               ray_subsample=333, seed=92, lin_out_bias=-3.0)
+        loss_fn = gu.block_masked_probe_loss
+    cpu_net, _ = syn.build_model(wl, "cpu")
+    sd = {k: v.clone() for k, v in cpu_net.state_dict().items() if not k.startswith("encoder.")}
+    got, _ = cuda_gradients(wl, sd, loss_fn=loss_fn)
+    lib = _lib.load()
+    assert lib.bts_last_bwd_kernel() == b"tc" and lib.bts_debug_tc_timeouts() == 0
+    ref = gu.oracle_gradients(wl, sd, loss_fn=loss_fn)
+    errs = {k: gu.rel_err(got[k], ref[k]) for k in ref}
+    print(variant, errs)
+    assert max(errs.values()) <= GRAD_REL_TOL, errs
