@@ -184,6 +184,7 @@ class ReconstructionLoss:
             raise NotImplementedError(f'criterion "{self.criterion_str}": the fused loss implements "l1+ssim" (every shipped config)')
         if use_automasking or self.median_thresholding or self.invalid_policy == "weight_guided_diverse":
             raise NotImplementedError("automasking / median thresholding / weight_guided_diverse are not implemented")
+        self._weights = {}       # device-resident loss-weight vectors, one per term layout
 
     @staticmethod
     def get_loss_metric_names():
@@ -203,84 +204,103 @@ class ReconstructionLoss:
         return ray.to(torch.float32), None
 
     def __call__(self, data):
+        """Every term is kept as (scalar tensor, weight in the loss, name of the logged sum, weight in that sum); the loss is
+        ONE stacked dot product with a cached weight vector and the logged scalars come from ONE device->host transfer
+        (the reference chains ~20 scalar kernels and calls ``.item()`` nine times, loss.py:169-291) -- the training step of
+        this path is host-bound, so launches matter."""
         with torch.autograd.profiler.record_function("loss_computation"):
             n_scales = len(data["coarse"])
             coarse_0 = data["coarse"][0]
-            inv_ray, inv_mass = self._invalid(coarse_0)
-            mask = dict(invalid_ray=inv_ray, invalid_mass=inv_mass) if self.ignore_invalid else {}
-            keep = None                                   # (n,pc,h,w) 1 - invalid, for the torch-side regularisers
-            if self.ignore_invalid:
-                keep = 1 - (inv_ray if inv_ray is not None else (inv_mass > .9).all(-1).to(torch.float32))
             rgb_gt = data["rgb_gt"]
-            zero = torch.zeros((), device=rgb_gt.device)
-            loss = zero
-            sums = {k: zero for k in ("coarse", "fine", "depth_reg", "alpha_reg", "surf", "eas", "depth_smooth")}
+            mask, keep_cache = {}, []
+            inv_ray = inv_mass = None
+            if self.ignore_invalid or self.lambda_entropy > 0:
+                inv_ray, inv_mass = self._invalid(coarse_0)
+            if self.ignore_invalid:
+                mask = dict(invalid_ray=inv_ray, invalid_mass=inv_mass)
+
+            def keep():        # (n,pc,h,w) 1 - invalid for the torch-side regularisers; built only if one of them is on
+                if not keep_cache:
+                    keep_cache.append(1 - (inv_ray if inv_ray is not None else (inv_mass > .9).all(-1).to(torch.float32)))
+                return keep_cache[0]
+
+            terms = []         # (tensor, loss weight, log name, log weight)
+            inv_s = 1.0 / n_scales                                                                          # :269
             for scale in range(n_scales):
                 coarse, fine = data["coarse"][scale], data["fine"][scale]
                 rgb_loss = patch_photometric_loss(coarse["rgb"], rgb_gt, **mask)[0]                       # :151-167
-                sums["coarse"] = sums["coarse"] + rgb_loss.detach() * self.lambda_coarse
-                if len(fine) > 0:                                                                         # :170-186
-                    if fine["rgb"] is coarse["rgb"]:
-                        fine_loss = rgb_loss
-                    else:
+                if len(fine) > 0 and fine["rgb"] is coarse["rgb"]:                                        # :170-186, trainer.py:246-247
+                    terms.append((rgb_loss, (self.lambda_coarse + self.lambda_fine) * inv_s, "loss_rgb_coarse", self.lambda_coarse))
+                    terms.append((None, 0.0, "loss_rgb_fine", self.lambda_fine))                          # same tensor as the previous term
+                else:
+                    terms.append((rgb_loss, self.lambda_coarse * inv_s if len(fine) > 0 else inv_s, "loss_rgb_coarse", self.lambda_coarse))
+                    if len(fine) > 0:
                         fmask = {}
                         if self.ignore_invalid:
                             fr, fm = self._invalid(data["fine"][0])
                             fmask = dict(invalid_ray=fr, invalid_mass=fm)
                         fine_loss = patch_photometric_loss(fine["rgb"], rgb_gt, **fmask)[0]
-                    sums["fine"] = sums["fine"] + fine_loss.detach() * self.lambda_fine
-                    rgb_loss = rgb_loss * self.lambda_coarse + fine_loss * self.lambda_fine
-                loss = loss + rgb_loss
+                        terms.append((fine_loss, self.lambda_fine * inv_s, "loss_rgb_fine", self.lambda_fine))
                 depths = coarse["depth"]
                 if self.lambda_depth_reg > 0:                                                             # :192-198
                     reg = (depths[:, :, 1:, :] - depths[:, :, :-1, :]).square().mean() + \
                           (depths[:, :, :, 1:] - depths[:, :, :, :-1]).square().mean()
-                    sums["depth_reg"] = sums["depth_reg"] + reg.detach()
-                    loss = loss + reg * self.lambda_depth_reg
+                    terms.append((reg, self.lambda_depth_reg * inv_s, "loss_depth_reg", 1.0))
                 if self.lambda_alpha_reg > 0:                                                             # :200-230
                     alphas = coarse["alphas"]
                     alpha_sum = alphas[..., :-1].sum(-1)
                     cap = torch.full_like(alpha_sum, alphas.shape[-1] * self.alpha_reg_fraction)
-                    if keep is not None:
-                        alpha_sum, cap = alpha_sum * keep, cap * keep
+                    if self.ignore_invalid:
+                        alpha_sum, cap = alpha_sum * keep(), cap * keep()
                     if self.alpha_reg_reduction == "ray":
                         reg = (alpha_sum - cap).clamp_min(0)
                     else:
                         reg = (alpha_sum.sum(-1) - cap.sum(-1)).clamp_min(0) / alpha_sum.shape[-1]
-                    reg = reg.mean()
-                    sums["alpha_reg"] = sums["alpha_reg"] + reg.detach()
-                    loss = loss + reg * self.lambda_alpha_reg
+                    terms.append((reg.mean(), self.lambda_alpha_reg * inv_s, "loss_alpha_reg", 1.0))
                 if self.lambda_surfaceness_reg > 0:                                                       # :232-245
                     alphas = coarse["alphas"]
                     sp = -torch.log(torch.exp(-alphas.abs()) + torch.exp(-(1 - alphas).abs())).mean(-1)
-                    if keep is not None:
-                        sp = sp * keep
-                    reg = sp.mean()
-                    sums["surf"] = sums["surf"] + reg.detach()
-                    loss = loss + reg * self.lambda_surfaceness_reg
+                    if self.ignore_invalid:
+                        sp = sp * keep()
+                    terms.append((sp.mean(), self.lambda_surfaceness_reg * inv_s, None, 0.0))
                 if self.lambda_edge_aware_smoothness > 0:                                                 # :247-259
                     eas = patch_edge_aware_smoothness(depths, rgb_gt, **mask)[0]
-                    sums["eas"] = sums["eas"] + eas.detach()
-                    loss = loss + eas * (self.lambda_edge_aware_smoothness / (2 ** scale))
+                    terms.append((eas, self.lambda_edge_aware_smoothness / (2 ** scale) * inv_s, "loss_eas", 1.0))
                 if self.lambda_depth_smoothness > 0:                                                      # :261-266
                     reg = (depths[..., :-1, :] - depths[..., 1:, :]).square().mean() + \
                           (depths[..., :, :-1] - depths[..., :, 1:]).square().mean()
-                    sums["depth_smooth"] = sums["depth_smooth"] + reg.detach()
-                    loss = loss + reg * self.lambda_depth_smoothness
-            loss = loss / n_scales                                                                        # :269
-            entropy = zero
+                    terms.append((reg, self.lambda_depth_smoothness * inv_s, "loss_depth_smoothness", 1.0))
             if self.lambda_entropy > 0:                                                                   # :271-281
                 import math
                 alphas = coarse_0["alphas"] + 1e-5
                 dens = alphas / alphas.sum(-1, keepdim=True)
                 ent = -(dens * torch.log(dens)).sum(-1) / math.log2(alphas.shape[-1])
-                ent = ent * (keep if keep is not None else 1.0)      # the reference masks unconditionally (:278)
-                entropy = ent.mean()
-                loss = loss + entropy * self.lambda_entropy
-            invalid_ratio = (1 - keep).mean() if keep is not None else zero
-        # one device->host transfer for all the logged scalars (the reference calls .item() nine times)
-        vals = torch.stack([sums["coarse"], sums["fine"], entropy.detach(), sums["depth_reg"], sums["alpha_reg"], sums["eas"],
-                            sums["depth_smooth"], invalid_ratio, loss.detach()]).tolist()
-        names = ["loss_rgb_coarse", "loss_rgb_fine", "loss_ray_entropy", "loss_depth_reg", "loss_alpha_reg", "loss_eas",
-                 "loss_depth_smoothness", "loss_invalid_ratio", "loss"]
-        return loss, dict(zip(names, vals))
+                ent = ent * keep()                                   # the reference masks with its invalid flags even when
+                terms.append((ent.mean(), self.lambda_entropy, "loss_ray_entropy", 1.0))   # ignore_invalid is off (:278)
+            # invalid ratio (:290): zero when the policy is "none"
+            if self.ignore_invalid:
+                ratio = inv_ray.mean() if inv_ray is not None else (inv_mass.amin(-1) > .9).to(torch.float32).mean()
+            else:
+                ratio = None
+
+            live = [t for t in terms if t[0] is not None]
+            stacked = torch.stack([t[0] for t in live])
+            key = (str(stacked.device), tuple(t[1] for t in live))
+            wvec = self._weights.get(key)
+            if wvec is None:
+                wvec = torch.tensor([t[1] for t in live], dtype=torch.float32, device=stacked.device)
+                self._weights[key] = wvec
+            loss = torch.dot(stacked, wvec)
+        host = torch.cat((stacked.detach(), loss.detach().view(1), (ratio if ratio is not None else loss.new_zeros(())).view(1))).tolist()
+        loss_dict = {k: 0.0 for k in ("loss_rgb_coarse", "loss_rgb_fine", "loss_ray_entropy", "loss_depth_reg", "loss_alpha_reg",
+                                      "loss_eas", "loss_depth_smoothness")}
+        i, last = 0, 0.0
+        for tensor, _, name, lw in terms:
+            if tensor is not None:
+                last = host[i]
+                i += 1
+            if name is not None:
+                loss_dict[name] += last * lw
+        loss_dict["loss_invalid_ratio"] = host[-1]
+        loss_dict["loss"] = host[-2]
+        return loss, loss_dict
