@@ -151,3 +151,30 @@ def test_reference_consumers_accept_the_output_contract():
     assert c["weights"].shape == (1, 2, H, W, 32) and c["invalid"].shape == (1, 2, H, W, 32, 1)
     z = proj_ops.distance_to_z(c["depth"], wl.Ks)
     assert z.shape == (1, 2, H, W) and torch.isfinite(z).all()
+
+
+@needs_ref
+def test_reconstruction_loss_constructor_matches_reference_class():
+    """behindthescenes_b200.loss.ReconstructionLoss parses the `loss:` config block exactly like the reference class
+    (models/bts/model/loss.py:44-77): same attribute names and values, same metric names, same rejection of a bad reduction."""
+    from oracle import ref_import
+    ref_import.load_reference()
+    import importlib
+    ref_cls = importlib.import_module("models.bts.model.loss").ReconstructionLoss
+    from behindthescenes_b200.loss import ReconstructionLoss
+    confs = [{"criterion": "l1+ssim", "invalid_policy": "weight_guided", "lambda_edge_aware_smoothness": 0.001},
+             {"criterion": "l1+ssim", "invalid_policy": "strict", "lambda_fine": 0.5, "lambda_entropy": 0.1, "lambda_depth_reg": 0.01,
+              "lambda_alpha_reg": 0.05, "lambda_surfaceness_reg": 0.02, "lambda_depth_smoothness": 0.03, "alpha_reg_fraction": 0.25,
+              "alpha_reg_reduction": "slice"},
+             {"criterion": "l1+ssim", "invalid_policy": "none"}]
+    names = ["criterion_str", "invalid_policy", "ignore_invalid", "lambda_coarse", "lambda_fine", "use_automasking", "lambda_entropy",
+             "lambda_depth_reg", "lambda_alpha_reg", "lambda_surfaceness_reg", "lambda_edge_aware_smoothness",
+             "lambda_depth_smoothness", "median_thresholding", "alpha_reg_reduction", "alpha_reg_fraction"]
+    for conf in confs:
+        ours, ref = ReconstructionLoss(conf), ref_cls(conf)
+        for nm in names:
+            assert getattr(ours, nm) == getattr(ref, nm), (conf, nm)
+    assert ReconstructionLoss.get_loss_metric_names() == ref_cls.get_loss_metric_names()
+    for cls in (ReconstructionLoss, ref_cls):
+        with pytest.raises(ValueError):
+            cls({"criterion": "l1+ssim", "alpha_reg_reduction": "patch"})
