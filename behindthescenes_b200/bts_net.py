@@ -71,6 +71,7 @@ class BTSNet(nn.Module):
         self._scale = 0
         self._encode_gen = 0
         self._scene_cache = {}
+        self._view_index_cache = {}
         self.grid_f_features = None
 
     # ------------------------------------------------------------------ reference API
@@ -88,11 +89,15 @@ class BTSNet(nn.Module):
         feature maps / cameras / colour images the render kernels read."""
         if combine_ids is not None:
             raise NotImplementedError("combine_ids (view groups) is not implemented on the B200 render path")
-        w2c = torch.inverse(poses_c2w)
+        # torch.inverse (models_bts.py:66) = linalg.inv_ex + a host-side check of the LU status, i.e. a device sync per
+        # frame that serialises the host with the previous step's kernels (2.8 of 4.6 ms of the training step's host time);
+        # same factorisation, same result, no sync -- a singular camera pose yields inf/nan instead of an exception
+        w2c = torch.linalg.inv_ex(poses_c2w, check_errors=False)[0]
         v = images.shape[1]
         ie = list(range(v)) if ids_encoder is None else list(ids_encoder)
         ir = list(range(v)) if ids_render is None else list(ids_render)
-        enc_in = images[:, ie]
+        take = self._take_views
+        enc_in = take(images, ie)
         colour_src = images_alt if images_alt is not None else images * 0.5 + 0.5
         n, nv, c, h, w = enc_in.shape
         flip = bool(self.flip_augmentation and self.training and (torch.rand(1) > 0.5).item())
@@ -105,8 +110,8 @@ class BTSNet(nn.Module):
         h_, w_ = latents[0].shape[-2:]
         c_l = self.encoder.latent_size
         self.grid_f_features = [F.interpolate(l, (h_, w_)).view(n, nv, c_l, h_, w_) for l in latents]
-        self.grid_f_Ks, self.grid_f_poses_w2c, self.grid_f_combine = Ks[:, ie], w2c[:, ie], None
-        self.grid_c_imgs, self.grid_c_Ks, self.grid_c_poses_w2c, self.grid_c_combine = colour_src[:, ir], Ks[:, ir], w2c[:, ir], None
+        self.grid_f_Ks, self.grid_f_poses_w2c, self.grid_f_combine = take(Ks, ie), take(w2c, ie), None
+        self.grid_c_imgs, self.grid_c_Ks, self.grid_c_poses_w2c, self.grid_c_combine = take(colour_src, ir), take(Ks, ir), take(w2c, ir), None
         # colour views that are the encoder view itself (eval_depth: ids_render == ids_encoder): the kernels reuse the
         # feature-view projection for them
         self._same_view_mask = 0
@@ -116,6 +121,20 @@ class BTSNet(nn.Module):
                     self._same_view_mask |= 1 << vi
         self._encode_gen += 1
         self._scene_cache.clear()
+
+    def _take_views(self, t, ids):
+        """``t[:, ids]`` (models_bts.py:75-81, :128-135) without the host sync: indexing a CUDA tensor with a Python list
+        uploads the index from pageable memory, which waits for every kernel already queued (3 ms of a 4.6 ms training
+        step went there).  Consecutive ids become a slice copy, anything else an ``index_select`` with a cached device index."""
+        ids = [int(i) for i in ids]
+        if len(ids) > 0 and ids == list(range(ids[0], ids[0] + len(ids))):
+            return t[:, ids[0]:ids[0] + len(ids)].clone()      # a fresh tensor, like advanced indexing returns
+        key = (str(t.device), tuple(ids))
+        idx = self._view_index_cache.get(key)
+        if idx is None:
+            idx = torch.tensor(ids, dtype=torch.long, device=t.device)
+            self._view_index_cache[key] = idx
+        return t.index_select(1, idx)
 
     def forward(self, xyz, coarse=True, viewdirs=None, far=False, only_density=False):
         """Point query (models_bts.py:266-338): xyz (n,P,3) -> rgb (n,P,3*Vc), invalid (n,P,Vc) float, sigma (n,P,1);

@@ -337,7 +337,7 @@ def run_ours(args):
             img_dev.copy_(img_host, non_blocking=True)                   # H2D: this frame's images, poses, intrinsics
             poses_dev.copy_(poses_host, non_blocking=True)
             Ks_dev.copy_(Ks_host, non_blocking=True)
-            net.grid_c_imgs = (img_dev * 0.5 + 0.5)[:, wl.ids_render]      # encode()'s colour cache (models_bts.py:81,133)
+            net.grid_c_imgs = net._take_views(img_dev * 0.5 + 0.5, wl.ids_render)   # encode()'s colour cache (models_bts.py:81,133); no list index: its H2D upload syncs the stream
             net.invalidate_scene()
             o = wrapped.render_views(poses_dev, Ks_dev, H_img, W_img, wl.model_conf["z_near"], wl.model_conf["z_far"],
                                      want_depth_z=True, **wants)["coarse"]
@@ -379,7 +379,7 @@ def run_ours(args):
             with torch.cuda.stream(s_c):
                 s_c.wait_event(ev_in[i])
                 net.grid_f_features = [feats_rot[i % len(feats_rot)]]
-                net.grid_c_imgs = (img_d[j] * 0.5 + 0.5)[:, wl.ids_render]
+                net.grid_c_imgs = net._take_views(img_d[j] * 0.5 + 0.5, wl.ids_render)
                 net.invalidate_scene()
                 o = wrapped.render_views(pos_d[j], Ks_d[j], H_img, W_img, wl.model_conf["z_near"], wl.model_conf["z_far"],
                                          want_depth_z=True, **wants)["coarse"]

@@ -48,6 +48,9 @@ def ours():
     gu.probe_loss(out).backward()
 
 
+HOST_MS = {}
+
+
 def timeit(fn, steps=10, warm=3):
     for _ in range(warm):
         fn()
@@ -55,10 +58,12 @@ def timeit(fn, steps=10, warm=3):
     if WORLD > 1:
         dist.barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
     a.record()
     for _ in range(steps):
         fn()
     b.record()
+    HOST_MS[fn.__name__] = (time.perf_counter() - t0) * 1e3 / steps      # host time to ENQUEUE a step (no sync inside)
     torch.cuda.synchronize()
     return a.elapsed_time(b) / steps
 
@@ -74,8 +79,21 @@ if WORLD > 1:
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0)
+if os.environ.get("PROFILE_HOST"):       # where the host time of a step goes
+    import cProfile, pstats, io
+    torch.cuda.synchronize()
+    pr = cProfile.Profile()
+    pr.enable()
+    for _ in range(20):
+        ours()
+    pr.disable()
+    torch.cuda.synchronize()
+    buf = io.StringIO()
+    pstats.Stats(pr, stream=buf).sort_stats("cumulative").print_stats(45)
+    print(buf.getvalue())
+    sys.exit(0)
 if os.environ.get("ONLY_OURS"):          # launch-list runs under ncu
-    print(json.dumps({"ms_ours": ms_ours, "loss": LOSS}))
+    print(json.dumps({"ms_ours": ms_ours, "host_enqueue_ms": HOST_MS.get("ours"), "loss": LOSS}))
     sys.exit(0)
 # reference op chain with autograd on the GPU
 from oracle import bts_oracle as orc
@@ -111,5 +129,5 @@ ms_ref = timeit(ref, steps=5, warm=2)
 g_ours = net.mlp_coarse.lin_in.weight.grad.detach().clone()
 g_ref = sdg["mlp_coarse.lin_in.weight"].grad
 print(json.dumps({"workload": f"cfg3-shaped training step: n={n} frames {H}x{W}, {R} rays each, K=64, Vc=2, fwd+bwd of the render path (encoder excluded), loss=" + LOSS,
-                  "ms_ours": ms_ours, "ms_reference_eager_gpu": ms_ref, "speedup": ms_ref / ms_ours,
+                  "ms_ours": ms_ours, "host_enqueue_ms_ours": HOST_MS.get("ours"), "ms_reference_eager_gpu": ms_ref, "host_enqueue_ms_reference": HOST_MS.get("ref"), "speedup": ms_ref / ms_ours,
                   "rays_per_s_ours": n * R / ms_ours * 1e3, "grad_rel_err_lin_in": gu.rel_err(g_ours.cpu(), g_ref.cpu())}))
