@@ -370,14 +370,21 @@ def run_ours(args):
             with torch.cuda.stream(s_in):
                 if i - slots in ev_out:
                     s_in.wait_event(ev_c[i - slots])                 # slot j's device inputs were consumed
-                if i == 3:
-                    t0.record(s_in)                                  # steps 0-2 fill the pipeline (untimed)
                 img_d[j].copy_(img_host, non_blocking=True)
                 pos_d[j].copy_(poses_host, non_blocking=True)
                 Ks_d[j].copy_(Ks_host, non_blocking=True)
                 ev_in[i] = torch.cuda.Event(); ev_in[i].record(s_in)
             with torch.cuda.stream(s_c):
                 s_c.wait_event(ev_in[i])
+                # steady-state period of the pipeline, taken on the compute stream: start of step 3 (steps 0-2 fill the
+                # pipeline) to start of step 3 + steps.  Every step in between waited for its own H2D (ev_in) and the host
+                # cannot run more than `slots` steps ahead of the D2H stream (ev_out.synchronize below), so transfer
+                # stalls show up in this period; recording on the copy streams instead would add up to `slots` steps of
+                # skew once the host no longer syncs every step.
+                if i == 3:
+                    t0.record(s_c)
+                if i == 3 + args.steps:
+                    t1.record(s_c)
                 net.grid_f_features = [feats_rot[i % len(feats_rot)]]
                 net.grid_c_imgs = net._take_views(img_d[j] * 0.5 + 0.5, wl.ids_render)
                 net.invalidate_scene()
@@ -392,8 +399,6 @@ def run_ours(args):
                 dep_h[j].copy_(o["depth_z"], non_blocking=True)
                 rgb_h[j].copy_(o["rgb"], non_blocking=True)
                 ev_out[i] = torch.cuda.Event(); ev_out[i].record(s_out)
-                if i == n_pipe - 4:
-                    t1.record(s_out)                                 # end of the last timed step (args.steps steps after t0)
             keep.pop(i - slots, None)
         torch.cuda.synchronize(dev)
         sync_all()
@@ -438,7 +443,7 @@ def run_ours(args):
                            "kernel": kernel_name, "ms_fold_pack": prep_ms, "ms_render": render_ms, "ms_metric_allreduce": metric_ms, "diag": diag},
                 "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": int(depth_host.numel() * 4 + rgb_host.numel() * 4), "ms_per_step": e2e_ms,
-                        "how": "3-stream pipeline (H2D | fold+pack+render | D2H), every step copies its own inputs and result",
+                        "how": "3-stream pipeline (H2D | fold+pack+render | D2H), every step copies its own inputs and result; steady-state period between compute starts of step 3 and step 3+steps",
                         "ms_per_step_unpipelined": e2e_seq_ms},
                 "gpu_launches": args.steps * (3 + 1),          # fold, fold_empty, pack_images, render per step (ours)
                 "roofline": roof, "clocks": clocks, "wall_s_timed_loop": wall,
