@@ -65,3 +65,48 @@ def test_smoothness_oracle_matches_reference_class_output():
         assert torch.allclose(depth.grad, f["cfg"][name]["grad_depth"], atol=1e-9, rtol=1e-5)
     # the fixture exercises the clamp and a flat patch
     assert (f["cfg"]["unmasked_slice"]["grad_depth"][0, 0, :2] == 0).all()
+
+
+import pytest
+
+
+@pytest.mark.parametrize("name", ["shipped", "all_terms", "unmasked_slice"])
+def test_reconstruction_loss_bookkeeping_on_cpu(name, monkeypatch):
+    """The host logic of behindthescenes_b200.loss.ReconstructionLoss (term weights, the fine = copy-of-coarse rule, the logged
+    sums, the masks handed to the fused ops) against the reference class fixture, with the two CUDA ops replaced by the
+    oracle -- in this test only; the GPU suite runs the same fixtures through the real kernels."""
+    from oracle.make_goldens import RECON_CONFIGS
+    from behindthescenes_b200 import loss as L
+
+    def fake_photo(rgb, rgb_gt, invalid_ray=None, invalid_mass=None, mass_thresh=0.9, **kw):
+        inv = invalid_ray if invalid_ray is not None else (None if invalid_mass is None else (invalid_mass > mass_thresh).all(-1))
+        loss, per_ray = lo.patch_loss(rgb, rgb_gt, None if inv is None else inv.reshape(rgb.shape[:4]))
+        return loss, per_ray
+
+    def fake_smooth(depth, rgb_gt, invalid_ray=None, invalid_mass=None, mass_thresh=0.9):
+        inv = invalid_ray if invalid_ray is not None else (None if invalid_mass is None else (invalid_mass > mass_thresh).all(-1))
+        return lo.smooth_loss(depth, rgb_gt, None if inv is None else inv.reshape(depth.shape))
+
+    monkeypatch.setattr(L, "patch_photometric_loss", fake_photo)
+    monkeypatch.setattr(L, "patch_edge_aware_smoothness", fake_smooth)
+    f = load_recon_fixture()
+    want = f["cfg"][name]
+    t = {k: v.clone() for k, v in f["in"].items()}
+    for k in ("rgb", "depth", "alphas"):
+        t[k].requires_grad_(True)
+    coarse = {k: t[k] for k in ("rgb", "depth", "alphas", "weights", "invalid")}
+    loss, loss_dict = L.ReconstructionLoss(RECON_CONFIGS[name])({"coarse": [coarse], "fine": [dict(coarse)], "rgb_gt": t["rgb_gt"]})
+    loss.backward()
+    assert abs(loss.item() - float(want["loss"])) < 1e-6 * max(1.0, abs(float(want["loss"])))
+    assert set(loss_dict) == set(want["dict"])
+    for k, v in want["dict"].items():
+        assert abs(loss_dict[k] - v) < 1e-6 * max(1.0, abs(v)), k
+    for k in ("rgb", "depth", "alphas"):
+        ref = want["grad_" + k]
+        got = t[k].grad if t[k].grad is not None else torch.zeros_like(ref)
+        assert torch.allclose(got, ref, rtol=1e-4, atol=1e-9 + 1e-6 * ref.abs().max().item()), k
+    if name == "shipped":       # the renderer's invalid_mass output may replace invalid + weights
+        mass = (f["in"]["invalid"] * f["in"]["weights"].unsqueeze(-1)).sum(-2)
+        c2 = {"rgb": f["in"]["rgb"], "depth": f["in"]["depth"], "invalid_mass": mass}
+        l2, d2 = L.ReconstructionLoss(RECON_CONFIGS[name])({"coarse": [c2], "fine": [dict(c2)], "rgb_gt": f["in"]["rgb_gt"]})
+        assert abs(l2.item() - float(want["loss"])) < 1e-6 and abs(d2["loss_invalid_ratio"] - want["dict"]["loss_invalid_ratio"]) < 1e-7
