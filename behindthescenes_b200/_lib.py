@@ -10,7 +10,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libbts_b200.so")
 
 BTS_MAX_BLOCKS = 8
-ABI_VERSION = 9
+ABI_VERSION = 10
 _fp = C.POINTER(C.c_float)
 
 
@@ -18,7 +18,8 @@ class BtsScene(C.Structure):
     _fields_ = [("n", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Hd", C.c_int32),
                 ("G", C.c_void_p), ("g_empty", C.c_void_p), ("K_f", C.c_void_p), ("w2c_f", C.c_void_p),
                 ("Vc", C.c_int32), ("Cc", C.c_int32), ("Hc", C.c_int32), ("Wc", C.c_int32),
-                ("img4", C.c_void_p), ("K_c", C.c_void_p), ("w2c_c", C.c_void_p), ("same_view_mask", C.c_int32)]
+                ("img4", C.c_void_p), ("K_c", C.c_void_p), ("w2c_c", C.c_void_p), ("same_view_mask", C.c_int32),
+                ("G16", C.c_void_p), ("g16_flags", C.c_void_p)]
 
 
 class BtsMlp(C.Structure):
@@ -35,13 +36,19 @@ class BtsRenderCfg(C.Structure):
                 ("learn_empty", C.c_int32), ("num_freqs", C.c_int32), ("include_input", C.c_int32),
                 ("freq_factor", C.c_float), ("z_near", C.c_float), ("z_far", C.c_float),
                 ("inv_z_far", C.c_float), ("inv_z_range", C.c_float), ("z_range", C.c_float),
-                ("z_steps", C.c_void_p), ("step", C.c_float), ("precision", C.c_int32)]
+                ("z_steps", C.c_void_p), ("step", C.c_float), ("band_mode", C.c_int32), ("precision", C.c_int32)]
 
 
 class BtsRenderOut(C.Structure):
     _fields_ = [("rgb", C.c_void_p), ("depth", C.c_void_p), ("invalid", C.c_void_p), ("weights", C.c_void_p),
                 ("alphas", C.c_void_p), ("z_samps", C.c_void_p), ("rgb_samps", C.c_void_p),
-                ("invalid_mass", C.c_void_p), ("sigma", C.c_void_p), ("depth_z", C.c_void_p)]
+                ("invalid_mass", C.c_void_p), ("sigma", C.c_void_p), ("depth_z", C.c_void_p),
+                ("scratch", C.c_void_p), ("scratch_ints", C.c_int64)]
+
+
+def band_scratch_ints(rays: int) -> int:
+    """BTS_BAND_SCRATCH_INTS of include/bts_b200.h."""
+    return 4 + (rays + 7) // 8
 
 
 class BtsRayGen(C.Structure):
@@ -67,6 +74,8 @@ EXPORTS = {
     "bts_debug_tc_timeouts": (C.c_int, []),
     "bts_fold_features": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bts_pack_g16": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bts_g16_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "bts_pack_images": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "bts_render_fwd": (C.c_int, [C.POINTER(BtsScene), C.POINTER(BtsMlp), C.POINTER(BtsRenderCfg), C.c_void_p,
                                  C.c_int64, C.c_int64, C.c_void_p, C.c_uint64, C.POINTER(BtsRenderOut), C.c_void_p]),

@@ -212,6 +212,7 @@ class BTSNet(nn.Module):
             steps = renderer._z_steps(K, dev)
             c.z_steps = steps.data_ptr()
             c.precision = int(getattr(renderer, "precision", 0))
+            c.band_mode = 0 if getattr(renderer, "band", True) else 1
             keep.append(steps)
         return c, keep
 
@@ -246,6 +247,13 @@ class BTSNet(nn.Module):
                                    None if efd is None else efd.data_ptr(), G.data_ptr(),
                                    None if g_empty is None else g_empty.data_ptr(), stream)
         _lib.check(rc, "bts_fold_features")
+        # operand-block copy of G for the band kernel (single-frame scenes: evaluation / novel-view rendering)
+        G16 = g16_flags = None
+        if n == 1 and Hd == 64 and getattr(self, "band_copy", True):
+            G16 = torch.empty((lib.bts_g16_bytes(n, H, W, Hd),), device=dev, dtype=torch.uint8)
+            g16_flags = torch.empty((1,), device=dev, dtype=torch.int32)
+            rc = lib.bts_pack_g16(G.data_ptr(), n, H, W, Hd, G16.data_ptr(), g16_flags.data_ptr(), stream)
+            _lib.check(rc, "bts_pack_g16")
         imgs = _dev_f32(self.grid_c_imgs.detach())
         _, Vc, Cc, Hc, Wc = imgs.shape
         img4 = torch.empty((n, Vc, Hc, Wc, 4), device=dev, dtype=torch.float32)
@@ -263,7 +271,9 @@ class BTSNet(nn.Module):
         s.Vc, s.Cc, s.Hc, s.Wc = Vc, Cc, Hc, Wc
         s.img4, s.K_c, s.w2c_c = img4.data_ptr(), Kc.data_ptr(), Mc.data_ptr()
         s.same_view_mask = int(getattr(self, "_same_view_mask", 0)) if (Hc, Wc) == (H, W) else 0
-        keep = [f, w, b_in, G, g_empty, efd, imgs, img4, Kf, Mf, Kc, Mc]
+        s.G16 = None if G16 is None else G16.data_ptr()
+        s.g16_flags = None if g16_flags is None else g16_flags.data_ptr()
+        keep = [f, w, b_in, G, g_empty, efd, imgs, img4, Kf, Mf, Kc, Mc, G16, g16_flags]
         self._scene_cache["scene"] = (key, s, keep)
         return s, keep
 
@@ -357,6 +367,10 @@ class BTSNet(nn.Module):
         out = _lib.BtsRenderOut()
         for k, t in ret.items():
             setattr(out, k, t.data_ptr())
+        if scene.G16:      # work list of the band kernel (groups it hands to the gather kernel); [0] = their count
+            ints = _lib.band_scratch_ints(n * R)
+            self._band_work = torch.empty((ints,), device=dev, dtype=torch.int32)
+            out.scratch, out.scratch_ints = self._band_work.data_ptr(), ints
         u_d = None
         if u is not None:
             u_d = _dev_f32(u.to(dev))

@@ -7,7 +7,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "lib", "libbts_b200.so")
-SOURCES = ["abi.cu", "fold.cu", "render_general.cu", "render_tc.cu", "render_bwd.cu", "fold_tc.cu", "patch_loss.cu", "fold_bwd_tc.cu", "render_bwd_tc.cu"]
+SOURCES = ["abi.cu", "fold.cu", "render_general.cu", "render_tc.cu", "render_band.cu", "render_bwd.cu", "fold_tc.cu", "patch_loss.cu", "fold_bwd_tc.cu", "render_bwd_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

@@ -27,6 +27,11 @@ cudaError_t launch_patch_loss(const PatchLossParams& p, bool backward, cudaStrea
 bool patch_loss_supported(int h, int w, int nv, int c);
 cudaError_t launch_patch_smooth(const PatchLossParams& p, bool backward, cudaStream_t stream);
 cudaError_t launch_pack_images(const float* img, int nv_total, int Cc, int Hc, int Wc, float* out, cudaStream_t stream);
+bool band_supported(const KernelParams& p);
+cudaError_t launch_band(const KernelParams& p, cudaStream_t stream);
+cudaError_t launch_pack_g16(const float* G, int n, int H, int W, int Hd, void* out, int32_t* flags, cudaStream_t stream);
+int64_t g16_bytes(int n, int H, int W, int Hd);
+int band_barrier_timeouts();
 }  // namespace bts
 
 namespace {
@@ -71,7 +76,22 @@ int bts_abi_version(void) { return BTS_ABI_VERSION; }
 const char* bts_last_error(void) { return g_err; }
 const char* bts_last_kernel(void) { return g_kernel; }
 const char* bts_last_bwd_kernel(void) { return g_bwd_kernel; }
-int bts_debug_tc_timeouts(void) { return bts::tc_barrier_timeouts() + bts::fold_barrier_timeouts() + bts::fold_bwd_barrier_timeouts() + bts::bwd_tc_barrier_timeouts(); }
+int bts_debug_tc_timeouts(void) {
+  return bts::tc_barrier_timeouts() + bts::fold_barrier_timeouts() + bts::fold_bwd_barrier_timeouts() + bts::bwd_tc_barrier_timeouts() +
+         bts::band_barrier_timeouts();
+}
+
+int64_t bts_g16_bytes(int32_t n, int32_t H, int32_t W, int32_t Hd) { return bts::g16_bytes(n, H, W, Hd); }
+
+int bts_pack_g16(const float* G, int32_t n, int32_t H, int32_t W, int32_t Hd, void* G16_out, int32_t* flags_out,
+                 bts_stream_t stream) {
+  if (!G || !G16_out || !flags_out) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_pack_g16: null pointer");
+  if (n < 1 || H < 1 || W < 1) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_pack_g16: bad sizes");
+  if (Hd != 64 && Hd != 128) return fail(BTS_ERR_UNSUPPORTED, "bts_pack_g16: d_hidden=%d must be 64 or 128", Hd);
+  const cudaError_t e = bts::launch_pack_g16(G, n, H, W, Hd, G16_out, flags_out, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_pack_g16: %s", cudaGetErrorString(e));
+  return BTS_OK;
+}
 
 int bts_fold_features(const float* feat_nchw, int32_t n, int32_t C, int32_t H, int32_t W, const float* w_in,
                       int32_t ld_w_in, const float* b_in, int32_t Hd, const float* empty_feature_or_null, float* G_out,
@@ -114,8 +134,19 @@ static int render_fwd_common(const char* who, const BtsScene* scene, const BtsMl
   if (gen) p.gen = *gen;
   p.p_pad = (mlp->P + 3) & ~3;
   cudaError_t e;
-  if (cfg->precision != 2 && bts::tc_supported(p)) {
+  if (out->scratch && out->scratch_ints >= BTS_BAND_SCRATCH_INTS(n * R)) p.work = out->scratch;
+  if (bts::tc_supported(p) && bts::band_supported(p)) {
+    // band kernel (feature fetch as tcgen05 MMAs over a TMA-staged band of G16); the 8-ray groups whose footprint does
+    // not fit are listed in `work` and rendered by the gather kernel right after it, same outputs
+    g_kernel = "band";
+    e = bts::launch_band(p, reinterpret_cast<cudaStream_t>(stream));
+    if (e == cudaSuccess) {
+      p.work_mode = 1;
+      e = bts::launch_tc(p, false, reinterpret_cast<cudaStream_t>(stream));
+    }
+  } else if (cfg->precision != 2 && bts::tc_supported(p)) {
     g_kernel = "tc";
+    p.work = nullptr;
     e = bts::launch_tc(p, false, reinterpret_cast<cudaStream_t>(stream));
   } else {
     if (cfg->precision == 1) return fail(BTS_ERR_UNSUPPORTED, "fast tier needs the tensor-core kernel (Hd=64, n_blocks=0, 6-octave code, K%%32==0)");

@@ -29,6 +29,8 @@ struct KernelParams {
   int64_t per_batch;     // R or P
   uint64_t seed;
   int p_pad;             // P rounded up to a multiple of 4
+  int32_t* work;         // band kernel: work[0] = number of 8-ray groups handed over, work[4 + i] = their indices
+  int work_mode;         // gather kernel: 1 = render only the 8-ray groups listed in `work` (after the band kernel)
 };
 
 // ------------------------------------------------------------------------------------------------------------------

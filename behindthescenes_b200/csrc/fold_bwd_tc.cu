@@ -140,7 +140,6 @@ __global__ void __launch_bounds__(kThreads, 1) fold_bwd_tc_kernel(const float* _
     }
   };
 
-  bool dead = false;                                       // bounded waits (bug guard), see render_tc.cu
   uint32_t full_phase[2] = {0, 0}, mma_phase = 0;
   int64_t tile = blockIdx.x;
   if (tid == 0 && use_map) tmap::prefetch_map(&feat_map);
@@ -155,7 +154,7 @@ __global__ void __launch_bounds__(kThreads, 1) fold_bwd_tc_kernel(const float* _
     const int64_t b = tile / tiles_per_b, p0 = (tile % tiles_per_b) * kTile;
     const int valid = (int)((HW - p0) < kTile ? (HW - p0) : kTile);
 
-    if (!dead && !tc::mbar_wait(&full[buf], full_phase[buf], 1u << 22)) { atomicAdd(&g_fold_bwd_barrier_timeouts, 1); dead = true; }
+    tc::mbar_wait_or_trap(&full[buf], full_phase[buf], &g_fold_bwd_barrier_timeouts);   // bounded: a pipeline bug traps instead of hanging or running on
     full_phase[buf] ^= 1u;
     const unsigned char* rawg = smem + Lt::kOffRawG + buf * Lt::kRawG;
     const unsigned char* rawf = smem + Lt::kOffRawF + buf * Lt::kRawF;
@@ -234,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1) fold_bwd_tc_kernel(const float* _
     }
     first = false;
     __syncwarp();
-    if (!dead && !tc::mbar_wait(mma_bar, mma_phase, 1u << 22)) { atomicAdd(&g_fold_bwd_barrier_timeouts, 1); dead = true; }
+    tc::mbar_wait_or_trap(mma_bar, mma_phase, &g_fold_bwd_barrier_timeouts);   // bounded: a pipeline bug traps instead of hanging or running on
     mma_phase ^= 1u;
     tc::tc_fence_after_sync();
     // ---- epilogue: dF[c, px] = D1[c, px] + D1[64 + c, px], stored as rows of the NCHW gradient ----

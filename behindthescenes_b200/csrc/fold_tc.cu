@@ -109,7 +109,6 @@ __global__ void __launch_bounds__(kThreads, 1) fold_tc_kernel(const float* __res
     for (int c = 0; c < C; ++c) bulk_load(dst + c * kTile * 4, src + (size_t)c * HW, row_bytes, &full[buf]);
   };
 
-  bool dead = false;                                       // bounded waits (bug guard), see render_tc.cu
   uint32_t full_phase[2] = {0, 0}, mma_phase = 0;
   int64_t tile = blockIdx.x;
   if (tid == 0 && use_map) tmap::prefetch_map(&feat_map);
@@ -121,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, 1) fold_tc_kernel(const float* __res
     const int64_t b = tile / tiles_per_b, p0 = (tile % tiles_per_b) * kTile;
     const int valid = (int)((HW - p0) < kTile ? (HW - p0) : kTile);
 
-    if (!dead && !tc::mbar_wait(&full[buf], full_phase[buf], 1u << 22)) { atomicAdd(&g_fold_barrier_timeouts, 1); dead = true; }
+    tc::mbar_wait_or_trap(&full[buf], full_phase[buf], &g_fold_barrier_timeouts);   // bounded: a pipeline bug traps instead of hanging or running on
     full_phase[buf] ^= 1u;
     // ---- transpose + split: thread = pixel row ----
     {
@@ -157,7 +156,7 @@ __global__ void __launch_bounds__(kThreads, 1) fold_tc_kernel(const float* __res
       tc::mma_commit(mma_bar);
     }
     __syncwarp();
-    if (!dead && !tc::mbar_wait(mma_bar, mma_phase, 1u << 22)) { atomicAdd(&g_fold_barrier_timeouts, 1); dead = true; }
+    tc::mbar_wait_or_trap(mma_bar, mma_phase, &g_fold_barrier_timeouts);   // bounded: a pipeline bug traps instead of hanging or running on
     mma_phase ^= 1u;
     tc::tc_fence_after_sync();
     // ---- epilogue: accumulator row + bias -> G ----

@@ -152,13 +152,13 @@ __global__ void __launch_bounds__(kThreads, 2) render_bwd_tc_kernel(const BwdPar
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
   uint32_t phase1 = 0, phase2 = 0;
-  bool wait_disabled = false, d2_pending = false, d2_started = false;
+  bool d2_pending = false, d2_started = false;
   const float b_out = __ldg(p.mlp.b_out);
   const bool use_empty = cfg.learn_empty && p.scene.g_empty != nullptr;
   const uint32_t idesc16 = tc::instr_desc(tc::kFmtF16, 128, HD), idesc32 = tc::instr_desc(tc::kFmtTF32, 128, HD);
   const uint32_t idescbf = tc::instr_desc(tc::kFmtBF16, 128, HD);
   auto wait_bar = [&](uint64_t* bar, uint32_t& phase) {
-    if (!wait_disabled && !tc::mbar_wait(bar, phase, 1u << 20)) { atomicAdd(&g_bwd_tc_barrier_timeouts, 1); wait_disabled = true; }
+    tc::mbar_wait_or_trap(bar, phase, &g_bwd_tc_barrier_timeouts);   // bounded: a pipeline bug traps (CUDA error) instead of hanging
     phase ^= 1u;
   };
 
@@ -183,7 +183,6 @@ __global__ void __launch_bounds__(kThreads, 2) render_bwd_tc_kernel(const BwdPar
     depth_bounds(p, ry, near_, far_);
     View vf;
     load_view(vf, p.scene.K_f + b * 9, p.scene.w2c_f + b * 16);
-    wait_disabled = wait_disabled || (*reinterpret_cast<volatile int*>(&g_bwd_tc_barrier_timeouts) != 0);
     if (lane < Vc * Cc) w_grgb[lane] = bp.g_rgb ? __ldg(bp.g_rgb + ray * Vc * Cc + lane) : 0.0f;
     const float g_depth = bp.g_depth ? __ldg(bp.g_depth + ray) : 0.0f;
     __syncwarp();

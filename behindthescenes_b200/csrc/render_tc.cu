@@ -83,6 +83,9 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_tc_kernel(
   constexpr int kGiStride = Lt::kGiStride, kLPS = Lt::kLanesPerSample, kSPI = Lt::kSamplesPerIter;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // work-list mode: render only the 8-ray groups the band kernel (render_band.cu) handed over; one group = 2 passes
+  const int work_groups = (!kPoints && p.work_mode) ? *reinterpret_cast<const volatile int32_t*>(p.work) : 0;
+  if (!kPoints && p.work_mode && (int)blockIdx.x >= 2 * work_groups) return;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8);
   float* s_wout = reinterpret_cast<float*>(smem + kOffWout);
@@ -136,7 +139,6 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_tc_kernel(
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes
   uint32_t bar_phase = 0;
-  bool wait_disabled = false;
 
   const int K = cfg.n_coarse, Vc = p.scene.Vc;
   const int H = p.scene.H, W = p.scene.W;
@@ -145,11 +147,16 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_tc_kernel(
   const uint32_t idesc16 = tc::instr_desc(tc::kFmtF16, 128, HD), idesc32 = tc::instr_desc(tc::kFmtTF32, 128, HD);
 
   const int64_t n_rays = p.n_items;                       // rays, or points in the query variant
-  const int64_t n_pass = kPoints ? (n_rays + 127) / 128 : (n_rays + 3) / 4;
+  const int64_t n_pass = kPoints ? (n_rays + 127) / 128 : ((!kPoints && p.work_mode) ? 2 * (int64_t)work_groups : (n_rays + 3) / 4);
+  // first ray of a pass (4 consecutive rays)
+  auto pass_base = [&](int64_t pass) -> int64_t {
+    if (!kPoints && p.work_mode) return (int64_t)__ldg(p.work + 4 + (pass >> 1)) * 8 + (pass & 1) * 4;
+    return pass * 4;
+  };
   View vf;
   load_view(vf, p.scene.K_f, p.scene.w2c_f);          // batch element 0; reloaded per ray only for batched scenes
   // the ray tensor row of the next pass is loaded one pass ahead (its latency hides behind a whole pass)
-  auto ray_of = [&](int64_t pass) { const int64_t r = pass * 4 + warp; return r < n_rays ? r : n_rays - 1; };
+  auto ray_of = [&](int64_t pass) { const int64_t r = pass_base(pass) + warp; return r < n_rays ? r : n_rays - 1; };
   float rv_next = (!kPoints && p.rays && lane < 8 && (int64_t)blockIdx.x < n_pass) ? __ldg(p.rays + ray_of(blockIdx.x) * 8 + lane) : 0.0f;
   for (int64_t pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
     // ---- per-pass setup: one ray per warp (render) or one point per lane (query) ----
@@ -158,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_tc_kernel(
     float ro0 = 0, ro1 = 0, ro2 = 0, rd0 = 0, rd1 = 0, rd2 = 0, near_ = 0, far_ = 0, zfac = 1.0f;
     float PX = 0, PY = 0, PZ = 0;
     if constexpr (!kPoints) {
-      const int64_t ray_raw = pass * 4 + warp;
+      const int64_t ray_raw = pass_base(pass) + warp;
       active = ray_raw < n_rays;
       ray = active ? ray_raw : n_rays - 1;
       b = p.scene.n == 1 ? 0 : ray / p.per_batch;   // 64-bit division only for batched scenes
@@ -177,7 +184,6 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_tc_kernel(
     }
     float T_carry = 1.0f, depth_part = 0.0f, wsum_part = 0.0f;
     for (int i = lane; i < kMaxColorViews * 5; i += 32) w_rgb[i] = 0.0f;
-    wait_disabled = wait_disabled || (*reinterpret_cast<volatile int*>(&g_tc_barrier_timeouts) != 0);
     if (p.scene.n != 1) load_view(vf, p.scene.K_f + b * 9, p.scene.w2c_f + b * 16);
 
     float z_ahead = kPoints ? 0.0f : sample_depth(p, ray, lane, near_, far_);   // depths are produced one chunk ahead
@@ -366,11 +372,9 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_tc_kernel(
       __syncwarp();
 
       // ---------------- P3: accumulator + interpolated row -> sigma ----------------
-      // bounded wait (bug guard): after the first expiry every later wait is skipped so a pipeline bug cannot hang the GPU
-      if (!wait_disabled && !tc::mbar_wait(bar, bar_phase, 1u << 20)) {
-        atomicAdd(&g_tc_barrier_timeouts, 1);
-        wait_disabled = true;
-      }
+      // bounded wait (bug guard): on expiry the kernel traps -- the launch fails with a CUDA error instead of hanging
+      // the GPU or reading an unfinished accumulator
+      tc::mbar_wait_or_trap(bar, bar_phase, &g_tc_barrier_timeouts);
       bar_phase ^= 1u;
       tc::tc_fence_after_sync();
       float logit = b_out;
@@ -469,7 +473,7 @@ static cudaError_t launch_tc_t(const KernelParams& p, cudaStream_t stream) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t n_pass = kPoints ? (p.n_items + 127) / 128 : (p.n_items + 3) / 4;
+  const int64_t n_pass = kPoints ? (p.n_items + 127) / 128 : (p.n_items + 3) / 4;   // work-list mode: upper bound
   const int64_t cap = (int64_t)sms * Lt::kCtasPerSm;      // persistent: every CTA resident, strided over passes
   const int grid = (int)(n_pass < cap ? n_pass : cap);
   kern<<<grid, tcr::kThreads, Lt::kSmemBytes, stream>>>(p);

@@ -26,12 +26,39 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {   // release.cta: prior shared-memory writes are visible to waiters
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // Bounded wait: returns false instead of hanging the GPU if the barrier never completes (bug guard).
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32_t max_spins = (1u << 24)) {
   for (uint32_t i = 0; i < max_spins; ++i)
     if (mbar_try_wait(bar, parity)) return true;
   return false;
 }
+
+// Unbounded-looking waits are bounded: a pipeline bug must not hang the GPU.  On expiry the kernel traps (the launch
+// fails with a CUDA error the ABI reports) instead of carrying on with unfinished data.
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity, int* timeout_counter) {
+  if (!mbar_wait(bar, parity, 1u << 22)) {
+    atomicAdd(timeout_counter, 1);
+    __trap();
+  }
+}
+// ---- bulk async copies (TMA engine, 1-D): global -> shared, completion counted in bytes on an mbarrier -----------
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// 16-byte asynchronous copy global -> shared (LDGSTS), completion via cp_async_wait_all
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // ---- proxies / fences --------------------------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

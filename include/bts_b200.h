@@ -13,6 +13,8 @@
  *   G      (n, H, W, Hd)      "folded feature map": G[p] = W_in[:, :C] * F[:, p] + b_in   (bts_fold_features)
  *   g_empty(Hd)               W_in[:, :C] * empty_feature + b_in                      (learn_empty)
  *   img4   (n, Vc, Hc, Wc, 4) colour views, channels-last padded to 4                (bts_pack_images)
+ *   G16    (n*H, ceil(W/8), 2, Hd/8, 8, 8) fp16: G as tcgen05 operand blocks, one per octet of 8 pixels:
+ *          [plane hi|lo][channel group][channel][pixel] (K-major core matrices, hi + lo = fp32-grade)  (bts_pack_g16)
  *   K_*    (n, V, 3, 3), w2c_* (n, V, 4, 4) row-major camera matrices as the reference caches them
  */
 #ifndef BTS_B200_H_
@@ -24,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BTS_ABI_VERSION 9
+#define BTS_ABI_VERSION 10
 #define BTS_MAX_BLOCKS 8   /* ResnetFC blocks supported by the kernels */
 
 typedef struct CUstream_st* bts_stream_t; /* == cudaStream_t */
@@ -53,6 +55,10 @@ typedef struct {
   const float* w2c_c;   /* (n, Vc, 4, 4)                                                */
   int32_t same_view_mask; /* bit v set: colour view v is the encoder view itself (same K, pose, size; eval_depth:
                              ids_render == ids_encoder) -> its projection and flags are reused, not recomputed */
+  const void* G16;        /* operand-block copy of G (bts_pack_g16) or NULL: enables the band kernel (bilinear
+                             interpolation of G on the tensor core from a TMA-staged pixel band)                     */
+  const int32_t* g16_flags; /* (1) device word written by bts_pack_g16: non-zero when a value of G does not fit fp16
+                             (the band kernel then hands every ray to the gather kernel)                            */
 } BtsScene;
 
 /* MLP = ResnetFC parameters (models/common/model/resnetfc.py:66-184), d_latent = 0, ReLU, d_out = 1.
@@ -93,6 +99,8 @@ typedef struct {
   float z_range;           /* float(d_max - d_min)                   models_bts.py:162   */
   const float* z_steps;    /* (K) device: torch.linspace(0, 1 - 1/K, K)   nerf.py:114    */
   float step;              /* float(1.0 / K)                              nerf.py:112    */
+  int32_t band_mode;       /* 0 = use the band kernel when scene.G16 and out.scratch are given and the shape allows,
+                              1 = never (gather kernel)                                                           */
   int32_t precision;       /* 0 = exact tier (tensor-core kernel with two-term operand split where the config
                               allows it, else the general fp32 kernel), 1 = fast tier (single-pass tensor core),
                               2 = exact tier forced onto the general CUDA-core kernel */
@@ -114,7 +122,11 @@ typedef struct {
                           node so that bts_render_bwd does not have to re-evaluate the MLP for the compositing pass  */
   float* depth_z;      /* (n, R)      z-depth = depth * (unit-ray z in its camera), utils/projection_operations.py:4-16;
                           only with in-kernel ray generation (BtsRayGen)                                            */
+  int32_t* scratch;    /* device work list of the band kernel or NULL: >= BTS_BAND_SCRATCH_INTS(n*R) ints.  After the call
+                          scratch[0] = number of 8-ray groups the band kernel handed to the gather kernel (debug)    */
+  int64_t scratch_ints;
 } BtsRenderOut;
+#define BTS_BAND_SCRATCH_INTS(rays) (4 + ((rays) + 7) / 8)
 
 /* In-kernel ray generation: replaces ImageRaySampler.sample -> util.gen_rays
  * (models/bts/model/ray_sampler.py:240-262, models/common/util/util.py:113-149, :244-273): one ray per pixel of every
@@ -141,6 +153,14 @@ int bts_fold_features(const float* feat_nchw, int32_t n, int32_t C, int32_t H, i
 /* (n, Vc, Cc, Hc, Wc) NCHW colour views (grid_c_imgs, models_bts.py:133) -> (n, Vc, Hc, Wc, 4) channels-last. */
 int bts_pack_images(const float* img_nchw, int32_t nv_total, int32_t Cc, int32_t Hc, int32_t Wc, float* img4_out,
                     bts_stream_t stream);
+
+/* G (n, H, W, Hd) fp32 -> G16 operand blocks (layout above; pixels past W are zero) and the fp16-range flag.
+ * Part of the encode-side glue like bts_fold_features: the bilinear feature fetch of models_bts.py:179 then runs as
+ * tcgen05 MMAs over a shared-memory band of these blocks.  Hd in {64, 128}. */
+int bts_pack_g16(const float* G, int32_t n, int32_t H, int32_t W, int32_t Hd, void* G16_out, int32_t* flags_out,
+                 bts_stream_t stream);
+/* bytes of the G16 buffer for a (n, H, W, Hd) map */
+int64_t bts_g16_bytes(int32_t n, int32_t H, int32_t W, int32_t Hd);
 
 /* Replaces _RenderWrapper.forward -> NeRFRenderer.forward -> sample_coarse + composite -> BTSNet.forward
  * (nerf.py:19-45, :315-375, :103-123, :210-313; models_bts.py:266-338) for the coarse pass.
@@ -234,7 +254,7 @@ int bts_patch_smooth_bwd(const float* depth, const float* gt, const float* inval
                          const float* invalid_mass_or_null, float mass_thresh, int64_t P, int32_t h, int32_t w, int32_t nv,
                          int32_t c, const float* g_per_ray, float* d_depth, bts_stream_t stream);
 
-/* Name of the kernel family the last bts_render_fwd on this thread dispatched to ("general" | "tc"), for tests. */
+/* Name of the kernel family the last bts_render_fwd on this thread dispatched to ("general" | "tc" | "band"), for tests. */
 const char* bts_last_kernel(void);
 /* Same for the last bts_render_bwd: "tc" (tensor-core backward: d_hidden 64, no blocks, saved sigma, K % 32 == 0) | "general". */
 const char* bts_last_bwd_kernel(void);

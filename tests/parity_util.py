@@ -19,9 +19,11 @@ def workload_from_golden(g):
                         rays=g.rays, u=g.u.reshape(-1, K))
 
 
-def cuda_render(wl, state_dict=None, device="cuda", use_u=True, precision=0, **wants):
+def cuda_render(wl, state_dict=None, device="cuda", use_u=True, precision=0, band=True, **wants):
+    """band=False keeps single-frame scenes on the gather kernel (render_tc.cu) instead of the band kernel."""
     net, wrapped = syn.build_model(wl, device, state_dict=state_dict)
     wrapped.renderer.precision = precision
+    wrapped.renderer.band = band
     with torch.no_grad():
         net.encode(wl.images.to(device), wl.Ks.to(device), wl.poses_c2w.to(device), ids_encoder=wl.ids_encoder,
                    ids_render=wl.ids_render)

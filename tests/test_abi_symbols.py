@@ -26,7 +26,7 @@ def _declared_functions():
 def test_header_declares_the_expected_entry_points():
     names = _declared_functions()
     for n in ("bts_abi_version", "bts_last_error", "bts_fold_features", "bts_pack_images", "bts_render_fwd",
-              "bts_query_field", "bts_last_kernel", "bts_render_bwd", "bts_render_views_fwd"):
+              "bts_query_field", "bts_last_kernel", "bts_render_bwd", "bts_render_views_fwd", "bts_pack_g16", "bts_g16_bytes"):
         assert n in names
 
 
@@ -35,18 +35,24 @@ def test_every_declared_symbol_is_exported(lib):
     for n in _declared_functions():
         assert hasattr(lib, n), f"{n} declared in include/bts_b200.h but not exported"
         assert n in _lib.EXPORTS, f"{n} has no ctypes prototype"
-    assert lib.bts_abi_version() == 9
+    assert lib.bts_abi_version() == 10
     assert lib.bts_last_error() is not None
 
 
 def test_struct_mirrors_match_header_layout():
     from behindthescenes_b200 import _lib
     # sizes under the LP64 C ABI: int32 fields, 8-byte pointers, natural alignment
-    assert ctypes.sizeof(_lib.BtsScene) == 16 + 4 * 8 + 16 + 3 * 8 + 8   # + same_view_mask (padded)
+    assert ctypes.sizeof(_lib.BtsScene) == 16 + 4 * 8 + 16 + 3 * 8 + 8 + 2 * 8   # + same_view_mask (padded), G16, g16_flags
     assert ctypes.sizeof(_lib.BtsMlp) == 16 + 2 * 8 + 4 * 8 * 8 + 2 * 8
-    assert ctypes.sizeof(_lib.BtsRenderOut) == 10 * 8
+    assert ctypes.sizeof(_lib.BtsRenderOut) == 10 * 8 + 8 + 8              # + scratch, scratch_ints
     assert ctypes.sizeof(_lib.BtsRayGen) == 2 * 8 + 4 * 4 + 2 * 4
-    assert ctypes.sizeof(_lib.BtsRenderCfg) == 9 * 4 + 6 * 4 + 4 + 8 + 8  # 9 ints, 6 floats, pad, ptr, step+precision
+    assert ctypes.sizeof(_lib.BtsRenderCfg) == 9 * 4 + 6 * 4 + 4 + 8 + 16  # 9 ints, 6 floats, pad, ptr, step+band_mode+precision+pad
+    assert lib_g16_bytes() == 2 * 192 * 81 * 2048        # two copies, ceil((640 + 4) / 8) blocks per row
+
+
+def lib_g16_bytes():
+    from behindthescenes_b200 import _lib
+    return _lib.load().bts_g16_bytes(1, 192, 640, 64)
 
 
 def test_argument_validation_without_gpu(lib):

@@ -47,21 +47,68 @@ def _last_kernel():
     return _lib.load().bts_last_kernel().decode()
 
 
-def test_tensor_core_kernel_is_dispatched_and_matches_general_kernel():
-    """cfg2 takes the tcgen05 kernel (exact tier); it must agree with the fp32 CUDA-core kernel and the oracle, and no
-    bounded barrier wait may expire."""
+def _handed_over(net):
+    """8-ray groups the band kernel passed on to the gather kernel in the last render (scratch[0])."""
+    return int(net._band_work[0].item())
+
+
+def test_tensor_core_kernels_are_dispatched_and_match_general_kernel():
+    """cfg2 takes the band kernel (exact tier; every tile of the stereo / same-view geometry fits the band), with
+    ``band=False`` the gather kernel; both must agree with the fp32 CUDA-core kernel and the oracle, and no bounded
+    barrier wait may expire."""
     wl = syn.cfg2_kitti360_eval(H=96, W=320, stereo=True, lin_out_bias=-4.0, seed=31, ray_subsample=20001)
     sd_net, _ = syn.build_model(wl, "cpu")
     sd = {k: v.clone() for k, v in sd_net.state_dict().items() if not k.startswith("encoder.")}
-    _, _, tc = pu.cuda_render(wl, state_dict=sd, precision=0, **ALL)
+    net, _, band = pu.cuda_render(wl, state_dict=sd, precision=0, **ALL)
+    assert _last_kernel() == "band"
+    print("groups handed to the gather kernel:", _handed_over(net), "of", (wl.rays.shape[1] + 7) // 8)
+    _, _, tc = pu.cuda_render(wl, state_dict=sd, precision=0, band=False, **ALL)
     assert _last_kernel() == "tc"
     _, _, gen = pu.cuda_render(wl, state_dict=sd, precision=2, **ALL)
     assert _last_kernel() == "general"
     assert _lib.load().bts_debug_tc_timeouts() == 0
     ref = pu.oracle_render(wl, sd, **ALL)
+    print("band vs oracle", pu.compare_render(wl, band, ref, label="band"))
     print("tc vs oracle", pu.compare_render(wl, tc, ref, label="tc"))
     print("general vs oracle", pu.compare_render(wl, gen, ref, label="general"))
+    print("band vs tc", pu.compare_render(wl, band, tc, label="band-vs-tc"))
     print("tc vs general", pu.compare_render(wl, tc, gen, label="tc-vs-general"))
+
+
+def test_band_kernel_covers_the_whole_frame_of_the_bench_geometry():
+    """Full consecutive-ray frame (the layout the band kernel is built for): encoder-view rays + stereo rays, no group
+    handed over, outputs within the exact tier of the oracle; in-kernel jitter is the same stream in both kernels."""
+    wl = syn.cfg2_kitti360_eval(H=64, W=208, stereo=True, lin_out_bias=-4.0, seed=33)
+    sd_net, _ = syn.build_model(wl, "cpu")
+    sd = {k: v.clone() for k, v in sd_net.state_dict().items() if not k.startswith("encoder.")}
+    wants = dict(want_weights=True, want_alphas=True)
+    net, _, band = pu.cuda_render(wl, state_dict=sd, **wants)
+    assert _last_kernel() == "band" and _handed_over(net) == 0
+    ref = pu.oracle_render(wl, sd, **wants)
+    print("band vs oracle", pu.compare_render(wl, band, ref, label="band-frame"))
+    _, _, b2 = pu.cuda_render(wl, state_dict=sd, use_u=False, **wants)
+    _, _, t2 = pu.cuda_render(wl, state_dict=sd, use_u=False, band=False, **wants)
+    print("band vs tc, in-kernel jitter", pu.compare_render(wl, b2, t2, label="band-vs-tc-seeded"))
+
+
+def test_band_kernel_hands_steep_epipolar_groups_to_the_gather_kernel():
+    """Rays of a camera displaced vertically and rolled: epipolar lines cross many rows, most tiles do not fit the band
+    -> the groups go through the work list and the gather kernel; results must be the oracle's either way."""
+    poses = [syn._pose(), syn._pose(tx=0.2, ty=0.45, tz=-0.3, yaw_deg=2.0, pitch_deg=4.0)]
+    wl = syn.make_workload("steep", H=64, W=208, poses=poses, model_conf=syn.kitti_model_conf(True),
+                           renderer_conf=syn.kitti_renderer_conf(64), ids_encoder=[0], ids_render=[0, 1], ray_views=[0, 1],
+                           seed=34, lin_out_bias=-4.0)
+    sd_net, _ = syn.build_model(wl, "cpu")
+    sd = {k: v.clone() for k, v in sd_net.state_dict().items() if not k.startswith("encoder.")}
+    net, _, got = pu.cuda_render(wl, state_dict=sd, **ALL)
+    assert _last_kernel() == "band"
+    n_groups = (wl.rays.shape[1] + 7) // 8
+    handed = _handed_over(net)
+    print("groups handed to the gather kernel:", handed, "of", n_groups)
+    assert 0 < handed < n_groups                # view-0 rays fit, most rays of the displaced camera do not
+    ref = pu.oracle_render(wl, sd, **ALL)
+    print("mixed band/gather vs oracle", pu.compare_render(wl, got, ref, label="steep"))
+    assert _lib.load().bts_debug_tc_timeouts() == 0
 
 
 def test_fast_tier_within_its_stated_tolerance():
