@@ -125,6 +125,28 @@ def load():
     return lib
 
 
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def on_device(dev):
+    """Context in which ``dev`` is the CURRENT CUDA device: the library launches on whatever device is current
+    (cudaGetDevice / cudaFuncSetAttribute / kernel<<<>>>), while the stream it is given belongs to the tensors' device --
+    a module living on cuda:1 with cuda:0 current (``model.to('cuda:1')`` without ``set_device``, or the autograd thread)
+    would otherwise launch on the wrong device."""
+    import torch
+    if dev.type != "cuda" or dev.index is None or torch.cuda.current_device() == dev.index:
+        return _NO_GUARD
+    return torch.cuda.device(dev)
+
+
 def check(rc: int, what: str):
     if rc == 0:
         return

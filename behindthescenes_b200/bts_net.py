@@ -154,14 +154,16 @@ class BTSNet(nn.Module):
         inv_f = torch.empty((n, P), device=dev, dtype=torch.float32)
         stream = torch.cuda.current_stream(dev).cuda_stream
         if only_density:
-            rc = lib.bts_query_field(C.byref(scene), C.byref(mlp), C.byref(cfg), xyz_d.data_ptr(), n, P, sigma.data_ptr(),
-                                     inv_f.data_ptr(), None, None, stream)
+            with _lib.on_device(dev):
+                rc = lib.bts_query_field(C.byref(scene), C.byref(mlp), C.byref(cfg), xyz_d.data_ptr(), n, P, sigma.data_ptr(),
+                                         inv_f.data_ptr(), None, None, stream)
             _lib.check(rc, "bts_query_field")
             return torch.zeros((n, P, Vc * 3), device=dev), inv_f.view(n, 1, P, 1), sigma
         rgb = torch.empty((n, P, Vc * Cc), device=dev, dtype=torch.float32)
         invalid = torch.empty((n, P, Vc), device=dev, dtype=torch.float32)
-        rc = lib.bts_query_field(C.byref(scene), C.byref(mlp), C.byref(cfg), xyz_d.data_ptr(), n, P, sigma.data_ptr(),
-                                 inv_f.data_ptr(), rgb.data_ptr(), invalid.data_ptr(), stream)
+        with _lib.on_device(dev):
+            rc = lib.bts_query_field(C.byref(scene), C.byref(mlp), C.byref(cfg), xyz_d.data_ptr(), n, P, sigma.data_ptr(),
+                                     inv_f.data_ptr(), rgb.data_ptr(), invalid.data_ptr(), stream)
         _lib.check(rc, "bts_query_field")
         return rgb, invalid, sigma
 
@@ -231,7 +233,7 @@ class BTSNet(nn.Module):
         b_p = self.mlp_coarse.lin_in.bias
         key = (self._encode_gen, self._scale, w_in._version, w_in.data_ptr(), b_p._version, feats._version, feats.data_ptr(),
                None if ef is None else (ef._version, ef.data_ptr()))
-        hit = self._scene_cache.get("scene")
+        hit = self._scene_cache.get(("scene", self._scale))   # one slot per scale (multiscale rendering, trainer.py:220-242)
         if hit is not None and hit[0] == key:
             return hit[1], hit[2]
         dev = feats.device
@@ -243,22 +245,25 @@ class BTSNet(nn.Module):
         G = torch.empty((n, H, W, Hd), device=dev, dtype=torch.float32)
         g_empty = torch.empty((Hd,), device=dev, dtype=torch.float32) if ef is not None else None
         efd = _dev_f32(ef.detach()) if ef is not None else None
-        rc = lib.bts_fold_features(f.data_ptr(), n, Cf, H, W, w.data_ptr(), w.shape[1], b_in.data_ptr(), Hd,
-                                   None if efd is None else efd.data_ptr(), G.data_ptr(),
-                                   None if g_empty is None else g_empty.data_ptr(), stream)
+        with _lib.on_device(dev):
+            rc = lib.bts_fold_features(f.data_ptr(), n, Cf, H, W, w.data_ptr(), w.shape[1], b_in.data_ptr(), Hd,
+                                       None if efd is None else efd.data_ptr(), G.data_ptr(),
+                                       None if g_empty is None else g_empty.data_ptr(), stream)
         _lib.check(rc, "bts_fold_features")
         # operand-block copy of G for the band kernel (single-frame scenes: evaluation / novel-view rendering)
         G16 = g16_flags = None
         if n == 1 and Hd == 64 and getattr(self, "band_copy", True):
             G16 = torch.empty((lib.bts_g16_bytes(n, H, W, Hd),), device=dev, dtype=torch.uint8)
             g16_flags = torch.empty((1,), device=dev, dtype=torch.int32)
-            rc = lib.bts_pack_g16(G.data_ptr(), n, H, W, Hd, G16.data_ptr(), g16_flags.data_ptr(), stream)
+            with _lib.on_device(dev):
+                rc = lib.bts_pack_g16(G.data_ptr(), n, H, W, Hd, G16.data_ptr(), g16_flags.data_ptr(), stream)
             _lib.check(rc, "bts_pack_g16")
         imgs = _dev_f32(self.grid_c_imgs.detach())
         _, Vc, Cc, Hc, Wc = imgs.shape
         img4 = torch.empty((n, Vc, Hc, Wc, 4), device=dev, dtype=torch.float32)
         if Vc > 0:
-            rc = lib.bts_pack_images(imgs.data_ptr(), n * Vc, Cc, Hc, Wc, img4.data_ptr(), stream)
+            with _lib.on_device(dev):
+                rc = lib.bts_pack_images(imgs.data_ptr(), n * Vc, Cc, Hc, Wc, img4.data_ptr(), stream)
             _lib.check(rc, "bts_pack_images")
         Kf = _dev_f32(self.grid_f_Ks[:, 0, :3, :3].detach())
         Mf = _dev_f32(self.grid_f_poses_w2c[:, 0].detach())
@@ -274,7 +279,7 @@ class BTSNet(nn.Module):
         s.G16 = None if G16 is None else G16.data_ptr()
         s.g16_flags = None if g16_flags is None else g16_flags.data_ptr()
         keep = [f, w, b_in, G, g_empty, efd, imgs, img4, Kf, Mf, Kc, Mc, G16, g16_flags]
-        self._scene_cache["scene"] = (key, s, keep)
+        self._scene_cache[("scene", self._scale)] = (key, s, keep)
         return s, keep
 
     def render_rays(self, renderer, rays, u=None, seed=0, want_weights=False, want_alphas=False, want_z_samps=False,
@@ -378,12 +383,14 @@ class BTSNet(nn.Module):
                 raise ValueError(f"u must have n*R*K = {n * R * K} elements, got {u_d.numel()}")
         stream = torch.cuda.current_stream(dev).cuda_stream
         if gen is None:
-            rc = lib.bts_render_fwd(C.byref(scene), C.byref(mlp), C.byref(cfg), rays_d.data_ptr(), n, R,
-                                    None if u_d is None else u_d.data_ptr(), int(seed) & (2 ** 64 - 1), C.byref(out), stream)
+            with _lib.on_device(dev):
+                rc = lib.bts_render_fwd(C.byref(scene), C.byref(mlp), C.byref(cfg), rays_d.data_ptr(), n, R,
+                                        None if u_d is None else u_d.data_ptr(), int(seed) & (2 ** 64 - 1), C.byref(out), stream)
             _lib.check(rc, "bts_render_fwd")
         else:
-            rc = lib.bts_render_views_fwd(C.byref(scene), C.byref(mlp), C.byref(cfg), C.byref(rg), n,
-                                          None if u_d is None else u_d.data_ptr(), int(seed) & (2 ** 64 - 1), C.byref(out), stream)
+            with _lib.on_device(dev):
+                rc = lib.bts_render_views_fwd(C.byref(scene), C.byref(mlp), C.byref(cfg), C.byref(rg), n,
+                                              None if u_d is None else u_d.data_ptr(), int(seed) & (2 ** 64 - 1), C.byref(out), stream)
             _lib.check(rc, "bts_render_views_fwd")
         return ret
 
@@ -396,6 +403,10 @@ class _RenderFunction(torch.autograd.Function):
     def forward(ctx, net, renderer, rays, u, seed, wants, keys, feats, w_in, b_in, w_out, b_out, empty, fc0_w, fc0_b, fc1_w, fc1_b):
         with torch.no_grad():
             out = net._render_rays_raw(renderer, rays, u=u, seed=seed, want_sigma=True, **wants)
+            # the scene this forward rendered (folded map of the current scale, cameras, colour views): the backward must
+            # scatter into / recompute against exactly this one, whatever set_scale() / encode() did in between
+            # (multiscale training renders scales 0..3 before one loss.backward(), trainer.py:220-242)
+            ctx.scene, ctx.scene_keep = net._scene_struct()
         ctx.net, ctx.renderer, ctx.seed, ctx.keys = net, renderer, seed, keys
         ctx.sigma = out.pop("sigma")
         ctx.has_u = u is not None
@@ -414,7 +425,7 @@ class _RenderFunction(torch.autograd.Function):
         lib = _lib.load()
         if int(renderer.n_coarse) != ctx.K:
             raise RuntimeError("renderer.n_coarse changed between forward and backward")
-        scene, keep = net._scene_struct()
+        scene, keep = ctx.scene, ctx.scene_keep             # forward-time scene (tensors kept alive by ctx)
         mlp, keep2 = net._mlp_struct()
         cfg, keep3 = net._cfg_struct(renderer)
         rays_d = _dev_f32(rays)
@@ -444,9 +455,10 @@ class _RenderFunction(torch.autograd.Function):
             pg.d_fc0_w, pg.d_fc0_b, pg.d_fc1_w, pg.d_fc1_b = (t.data_ptr() for t in dblk)
         u_d = _dev_f32(u.to(dev)) if ctx.has_u else None
         stream = torch.cuda.current_stream(dev).cuda_stream
-        rc = lib.bts_render_bwd(C.byref(scene), C.byref(mlp), C.byref(cfg), rays_d.data_ptr(), n, R,
-                                None if u_d is None else u_d.data_ptr(), int(ctx.seed) & (2 ** 64 - 1),
-                                ctx.sigma.data_ptr(), C.byref(up), C.byref(pg), stream)
+        with _lib.on_device(dev):
+            rc = lib.bts_render_bwd(C.byref(scene), C.byref(mlp), C.byref(cfg), rays_d.data_ptr(), n, R,
+                                    None if u_d is None else u_d.data_ptr(), int(ctx.seed) & (2 ** 64 - 1),
+                                    ctx.sigma.data_ptr(), C.byref(up), C.byref(pg), stream)
         _lib.check(rc, "bts_render_bwd")
         # dense tail of the fold G = F W_F^T + b_in (two plain GEMMs)
         nb, _, _, H, W = feats.shape
@@ -460,8 +472,9 @@ class _RenderFunction(torch.autograd.Function):
         if feats_c.dtype == torch.float32 and feats_c.is_contiguous() and w_c.dtype == torch.float32 and w_c.stride(1) == 1:
             d_feats = torch.empty_like(feats_c) if need_df else None
             d_WF, d_b = d_WF_acc, d_b_acc
-            rc = lib.bts_fold_features_bwd(dG.data_ptr(), feats_c.data_ptr(), nb, Cf, H, W, w_c.data_ptr(), w_c.stride(0), Hd,
-                                           d_feats.data_ptr() if need_df else None, d_WF.data_ptr(), d_b.data_ptr(), stream)
+            with _lib.on_device(dev):
+                rc = lib.bts_fold_features_bwd(dG.data_ptr(), feats_c.data_ptr(), nb, Cf, H, W, w_c.data_ptr(), w_c.stride(0), Hd,
+                                               d_feats.data_ptr() if need_df else None, d_WF.data_ptr(), d_b.data_ptr(), stream)
             if rc == 0:
                 d_b_in = d_b + dge
             elif rc == -2:          # shape outside the tensor-core fold backward: dense formulation below

@@ -35,17 +35,18 @@ struct KernelParams {
 
 // ------------------------------------------------------------------------------------------------------------------
 // Counter-based generator for the stratified jitter when the caller does not inject `u`
-// (the reference draws torch.rand_like, models/common/render/nerf.py:116).  Stateless: two rounds of the murmur3
-// 32-bit finaliser over (seed, ray, sample) -- every (ray, sample) gets an independent-looking uniform, reproducible
-// per seed, ~14 instructions.  uniform = top 24 bits * 2^-24 in [0,1) like torch's float uniform.
+// (the reference draws torch.rand_like, models/common/render/nerf.py:116).  Stateless: the murmur3 32-bit finaliser
+// over a word that mixes (seed, ray, sample) with odd multipliers -- every (ray, sample) gets an independent-looking
+// uniform, reproducible per seed, ~10 instructions.  uniform = top 24 bits * 2^-24 in [0,1) like torch's float uniform.
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
   h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
   return h;
 }
 __device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t ray, uint32_t k) {
-  uint32_t h = fmix32((uint32_t)ray ^ (uint32_t)seed);
-  h = fmix32(h ^ ((uint32_t)(ray >> 32) * 0x9E3779B1u) ^ (k * 0x85EBCA77u + 0x165667B1u) ^ (uint32_t)(seed >> 32));
+  uint32_t h = (uint32_t)ray * 0x9E3779B1u + k * 0x85EBCA77u + (uint32_t)seed;
+  h ^= (uint32_t)(ray >> 32) * 0xC2B2AE3Du + (uint32_t)(seed >> 32) * 0x27D4EB2Fu;
+  h = fmix32(h ^ 0x165667B1u);
   return (float)(h >> 8) * (1.0f / 16777216.0f);
 }
 

@@ -89,6 +89,20 @@ __device__ __forceinline__ float seg16_sum(float v) {   // sum over the 16 lanes
   for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
   return v;
 }
+// packed fp32 pairs (Blackwell FFMA2: one issue slot for two fused multiply-adds)
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void ffma2(uint64_t& acc, uint64_t a, uint64_t b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ float2 unpack2(uint64_t v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
 __device__ __forceinline__ void group_sync(int group) {   // barrier over the 4 warps of a tile group
   asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kGroupThreads) : "memory");
 }
@@ -348,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
       return g;
     };
     auto issue_band = [&](const Geom& g) {   // one bulk copy per band row: `no` consecutive blocks of G16
-      if (gt == 0 && g.nsteps > 0) {
+      if (gt == 32 && g.nsteps > 0) {      // warp 1 (warp 0 issues the MMAs)
         const uint32_t row_bytes = (uint32_t)g.no * Lt::kBlk;
         const int rows_all = 2 * (g.nsteps / g.no);
         const int nrows = rows_all < H - g.yb ? rows_all : H - g.yb;
@@ -457,7 +471,7 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
 
     for (int c0 = 0; c0 < K; c0 += 16) {
       const int k = c0 + hl;
-      const int64_t sample_id = (int64_t)ray * K + k;
+      const uint32_t sample_id = (uint32_t)ray * (uint32_t)K + (uint32_t)k;   // < 2^31 elements per output (launcher)
       group_sync(group);                   // operands of this tile complete; the previous tile is fully consumed
       // ---------------- MMA issue (one thread of the group) ----------------
       if (gt == 0) {
@@ -529,7 +543,7 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
       const bool inv_f = (tap.bits >> 26) & 1, empty_me = (tap.bits >> 27) & 1, big = (tap.bits >> 28) & 1;
       float logit = b_out;
       if (!__any_sync(kFull, big || empty_me)) {           // warp-uniform: tcgen05.ld is warp-collective
-        float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;   // four independent chains (ILP)
+        uint64_t l01 = pack2(0.0f, 0.0f), l23 = l01, l45 = l01, l67 = l01;   // 8 chains in 4 packed accumulators
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {                    // 32 accumulator columns at a time (register budget)
           uint32_t dv[2][16];
@@ -540,15 +554,17 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float4 wv = wo4[c * 4 + e];
-              l0 = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 0]), 0.0f), wv.x, l0);
-              l1 = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 1]), 0.0f), wv.y, l1);
-              l2 = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 2]), 0.0f), wv.z, l2);
-              l3 = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 3]), 0.0f), wv.w, l3);
+            for (int e = 0; e < 4; e += 2) {
+              const float4 wa = wo4[c * 4 + e], wb = wo4[c * 4 + e + 1];
+              ffma2(l01, pack2(fmaxf(__uint_as_float(dv[c][e * 4 + 0]), 0.0f), fmaxf(__uint_as_float(dv[c][e * 4 + 1]), 0.0f)), pack2(wa.x, wa.y));
+              ffma2(l23, pack2(fmaxf(__uint_as_float(dv[c][e * 4 + 2]), 0.0f), fmaxf(__uint_as_float(dv[c][e * 4 + 3]), 0.0f)), pack2(wa.z, wa.w));
+              ffma2(l45, pack2(fmaxf(__uint_as_float(dv[c][e * 4 + 4]), 0.0f), fmaxf(__uint_as_float(dv[c][e * 4 + 5]), 0.0f)), pack2(wb.x, wb.y));
+              ffma2(l67, pack2(fmaxf(__uint_as_float(dv[c][e * 4 + 6]), 0.0f), fmaxf(__uint_as_float(dv[c][e * 4 + 7]), 0.0f)), pack2(wb.z, wb.w));
             }
           }
         }
+        const float2 s01 = unpack2(l01), s23 = unpack2(l23), s45 = unpack2(l45), s67 = unpack2(l67);
+        const float l0 = s01.x + s45.x, l1 = s01.y + s45.y, l2 = s23.x + s67.x, l3 = s23.y + s67.y;
         logit += (l0 + l1) + (l2 + l3);
       } else {   // rare: learned empty row and/or the raw-coordinate part of lin_in added in fp32 (code recomputed)
         float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f;
@@ -620,7 +636,7 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
             }
             float col[4] = {0, 0, 0, 0};
             if (active) {
-              const float4* base = reinterpret_cast<const float4*>(p.scene.img4) + ((int64_t)v * Hc + y0) * Wc + x0;
+              const float4* base = reinterpret_cast<const float4*>(p.scene.img4) + (uint32_t)((v * Hc + y0) * Wc + x0);
               const float4 c00 = __ldg(base), c01 = __ldg(base + dx);
               const float4 c10 = __ldg(base + dy * Wc), c11 = __ldg(base + dy * Wc + dx);
               const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
@@ -632,11 +648,11 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
             }
             const float inv = (inv_c | inv_f) ? 1.0f : 0.0f;   // :333-334
             if (active) {
-              if (p.out.invalid) p.out.invalid[sample_id * Vc + v] = inv;
+              if (p.out.invalid) p.out.invalid[sample_id * (uint32_t)Vc + v] = inv;
               if (p.out.rgb_samps) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
-                  if (c < Cc) p.out.rgb_samps[(sample_id * Vc + v) * Cc + c] = col[c];
+                  if (c < Cc) p.out.rgb_samps[(sample_id * (uint32_t)Vc + v) * (uint32_t)Cc + c] = col[c];
               }
             }
 #pragma unroll
@@ -728,7 +744,9 @@ bool band_supported(const KernelParams& p) {
   const BtsRenderCfg& c = p.cfg;
   return p.scene.G16 != nullptr && p.work != nullptr && p.scene.n == 1 && p.mlp.Hd == 64 && p.mlp.n_blocks == 0 &&
          p.mlp.P == 39 && c.num_freqs == 6 && c.include_input && c.n_coarse % 16 == 0 && c.n_coarse <= band::kMaxK &&
-         p.scene.Vc <= band::kViews && p.scene.H <= 4096 && p.scene.W <= 4096 && p.n_items < (int64_t)0x7fffffff &&
+         p.scene.Vc <= band::kViews && p.scene.H <= 4096 && p.scene.W <= 4096 &&
+         p.n_items * c.n_coarse * (p.scene.Vc > 0 ? p.scene.Vc * p.scene.Cc : 1) < (int64_t)0x7fffffff &&   // 32-bit output indices
+         (int64_t)p.scene.Vc * p.scene.Hc * p.scene.Wc < (int64_t)0x7fffffff &&
          c.band_mode == 0 && c.precision == 0 && p.xyz == nullptr &&
          (reinterpret_cast<uintptr_t>(p.rays) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.scene.G16) & 15) == 0 &&
          (reinterpret_cast<uintptr_t>(p.scene.img4) & 15) == 0;

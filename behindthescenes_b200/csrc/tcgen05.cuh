@@ -36,13 +36,26 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32
   return false;
 }
 
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or ~`ns` nanoseconds pass,
+// instead of burning issue slots in a spin loop
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 // Unbounded-looking waits are bounded: a pipeline bug must not hang the GPU.  On expiry the kernel traps (the launch
 // fails with a CUDA error the ABI reports) instead of carrying on with unfinished data.
 __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity, int* timeout_counter) {
-  if (!mbar_wait(bar, parity, 1u << 22)) {
-    atomicAdd(timeout_counter, 1);
-    __trap();
-  }
+  for (uint32_t i = 0; i < (1u << 20); ++i)
+    if (mbar_try_wait_hint(bar, parity, 2000u)) return;      // <= ~2 s in total
+  atomicAdd(timeout_counter, 1);
+  __trap();
 }
 // ---- bulk async copies (TMA engine, 1-D): global -> shared, completion counted in bytes on an mbarrier -----------
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {

@@ -30,11 +30,12 @@ class _PatchLoss(torch.autograd.Function):
         argmin = torch.empty((n, pc, h, w), device=pred.device, dtype=torch.int32)
         errors = torch.empty((n, pc, h, w, nv), device=pred.device, dtype=torch.float32) if want_errors else None
         stream = torch.cuda.current_stream(pred.device).cuda_stream
-        _lib.check(lib.bts_patch_loss_fwd(pred.data_ptr(), gt.data_ptr(),
-                                          invalid_ray.data_ptr() if invalid_ray is not None else None,
-                                          invalid_mass.data_ptr() if invalid_mass is not None else None,
-                                          float(mass_thresh), P, h, w, nv, c, per_ray.data_ptr(), argmin.data_ptr(),
-                                          errors.data_ptr() if errors is not None else None, stream), "bts_patch_loss_fwd")
+        with _lib.on_device(pred.device):
+            _lib.check(lib.bts_patch_loss_fwd(pred.data_ptr(), gt.data_ptr(),
+                                              invalid_ray.data_ptr() if invalid_ray is not None else None,
+                                              invalid_mass.data_ptr() if invalid_mass is not None else None,
+                                              float(mass_thresh), P, h, w, nv, c, per_ray.data_ptr(), argmin.data_ptr(),
+                                              errors.data_ptr() if errors is not None else None, stream), "bts_patch_loss_fwd")
         ctx.save_for_backward(pred, gt, invalid_ray, invalid_mass, argmin)
         ctx.mass_thresh = float(mass_thresh)
         ctx.mark_non_differentiable(argmin)
@@ -50,11 +51,12 @@ class _PatchLoss(torch.autograd.Function):
         g = _f32c(g_per_ray)
         d_pred = torch.empty_like(pred)
         stream = torch.cuda.current_stream(pred.device).cuda_stream
-        _lib.check(lib.bts_patch_loss_bwd(pred.data_ptr(), gt.data_ptr(),
-                                          invalid_ray.data_ptr() if invalid_ray is not None else None,
-                                          invalid_mass.data_ptr() if invalid_mass is not None else None,
-                                          ctx.mass_thresh, n * pc, h, w, nv, c, argmin.data_ptr(), g.data_ptr(),
-                                          d_pred.data_ptr(), stream), "bts_patch_loss_bwd")
+        with _lib.on_device(pred.device):
+            _lib.check(lib.bts_patch_loss_bwd(pred.data_ptr(), gt.data_ptr(),
+                                              invalid_ray.data_ptr() if invalid_ray is not None else None,
+                                              invalid_mass.data_ptr() if invalid_mass is not None else None,
+                                              ctx.mass_thresh, n * pc, h, w, nv, c, argmin.data_ptr(), g.data_ptr(),
+                                              d_pred.data_ptr(), stream), "bts_patch_loss_bwd")
         return d_pred, None, None, None, None, None
 
 
@@ -103,11 +105,12 @@ class _PatchSmooth(torch.autograd.Function):
         c = gt.shape[-1]
         per_ray = torch.empty_like(depth)
         stream = torch.cuda.current_stream(depth.device).cuda_stream
-        _lib.check(lib.bts_patch_smooth_fwd(depth.data_ptr(), gt.data_ptr(),
-                                            invalid_ray.data_ptr() if invalid_ray is not None else None,
-                                            invalid_mass.data_ptr() if invalid_mass is not None else None,
-                                            float(mass_thresh), n * pc, h, w, nv, c, per_ray.data_ptr(), stream),
-                   "bts_patch_smooth_fwd")
+        with _lib.on_device(depth.device):
+            _lib.check(lib.bts_patch_smooth_fwd(depth.data_ptr(), gt.data_ptr(),
+                                                invalid_ray.data_ptr() if invalid_ray is not None else None,
+                                                invalid_mass.data_ptr() if invalid_mass is not None else None,
+                                                float(mass_thresh), n * pc, h, w, nv, c, per_ray.data_ptr(), stream),
+                       "bts_patch_smooth_fwd")
         ctx.save_for_backward(depth, gt, invalid_ray, invalid_mass)
         ctx.mass_thresh, ctx.nv = float(mass_thresh), nv
         return per_ray
@@ -120,11 +123,12 @@ class _PatchSmooth(torch.autograd.Function):
         g = _f32c(g_per_ray)
         d_depth = torch.empty_like(depth)
         stream = torch.cuda.current_stream(depth.device).cuda_stream
-        _lib.check(lib.bts_patch_smooth_bwd(depth.data_ptr(), gt.data_ptr(),
-                                            invalid_ray.data_ptr() if invalid_ray is not None else None,
-                                            invalid_mass.data_ptr() if invalid_mass is not None else None,
-                                            ctx.mass_thresh, n * pc, h, w, ctx.nv, gt.shape[-1], g.data_ptr(), d_depth.data_ptr(),
-                                            stream), "bts_patch_smooth_bwd")
+        with _lib.on_device(depth.device):
+            _lib.check(lib.bts_patch_smooth_bwd(depth.data_ptr(), gt.data_ptr(),
+                                                invalid_ray.data_ptr() if invalid_ray is not None else None,
+                                                invalid_mass.data_ptr() if invalid_mass is not None else None,
+                                                ctx.mass_thresh, n * pc, h, w, ctx.nv, gt.shape[-1], g.data_ptr(), d_depth.data_ptr(),
+                                                stream), "bts_patch_smooth_bwd")
         return d_depth, None, None, None, None, None
 
 
@@ -144,6 +148,13 @@ def patch_edge_aware_smoothness(depth, rgb_gt, invalid_ray=None, invalid_mass=No
         invalid_mass = _f32c(invalid_mass.reshape(n, pc, h, w, nv))
     per_ray = _PatchSmooth.apply(_f32c(depth), gt, invalid_ray, invalid_mass, mass_thresh, nv)
     return per_ray.mean(), per_ray
+
+
+def _same_tensor(a: torch.Tensor, b: torch.Tensor) -> bool:
+    """Do ``a`` and ``b`` hold the same values by construction?  The trainer aliases ``fine`` to ``coarse`` when there is
+    no fine pass (trainer.py:246-247), but ``PatchRaySampler.reconstruct`` (ray_sampler.py:189-195) then replaces both
+    entries with separate ``.view()`` objects of one buffer -- identity fails, storage + layout does not."""
+    return a is b or (a.data_ptr() == b.data_ptr() and a.shape == b.shape and a.stride() == b.stride() and a.dtype == b.dtype)
 
 
 class ReconstructionLoss:
@@ -229,7 +240,7 @@ class ReconstructionLoss:
             for scale in range(n_scales):
                 coarse, fine = data["coarse"][scale], data["fine"][scale]
                 rgb_loss = patch_photometric_loss(coarse["rgb"], rgb_gt, **mask)[0]                       # :151-167
-                if len(fine) > 0 and fine["rgb"] is coarse["rgb"]:                                        # :170-186, trainer.py:246-247
+                if len(fine) > 0 and _same_tensor(fine["rgb"], coarse["rgb"]):                            # :170-186, trainer.py:246-247
                     terms.append((rgb_loss, (self.lambda_coarse + self.lambda_fine) * inv_s, "loss_rgb_coarse", self.lambda_coarse))
                     terms.append((None, 0.0, "loss_rgb_fine", self.lambda_fine))                          # same tensor as the previous term
                 else:
