@@ -8,9 +8,15 @@
 Workload at N=1 = BASELINE config 2 ("KITTI-360 eval_depth: 192x640, 64 samples/ray"): one stereo frame as
 ``models/bts/evaluator.py:62-68`` renders it -- rays of both views (245 760 rays), encoder view 0, one colour view,
 ``want_weights=True, want_alphas=True``.  A step = one pass of the hot path over that ray batch: fold of the frame's
-feature map (our per-frame glue), colour packing and the fused render launch.  ``encode`` (the ResNet) is excluded
-from the metric as in BASELINE.md.  At N>1 every rank renders its own block of an N-times larger global ray batch
-(``behindthescenes_b200.rays.shard_rays``; scene replicated) and the per-step scalar metric is all-reduced over NCCL.
+feature map + its operand-block copy (our per-frame glue), colour packing and the fused render launch (band kernel +
+the work-list pass of the gather kernel).  ``encode`` (the ResNet) is excluded from the metric as in BASELINE.md.  At N>1
+every rank renders its own block of an N-times larger global ray batch (``behindthescenes_b200.rays.shard_rays``; scene
+replicated; weak scaling) and the scalar metric (depth sum, ray count) is accumulated on the device on a side stream and
+all-reduced over NCCL once, off the critical path (the reference's ``sync_all_reduce`` runs once per epoch too,
+``utils/metrics.py:31``).
+
+Extra keys of the same JSON line (``"extra"``, skipped with ``--no-extras``): strong scaling of ONE cfg2 frame and of the
+cfg5 ray batch over the ranks, the cfg3 training step (weak), the cfg4 render -- ``tools/bench_workloads.py``.
 
 Timing: per-step CUDA events on the launching stream (torch's current stream), an L2 flush (256 MiB write) before
 every timed step outside the event pair, max over ranks.  See DESIGN.md "Measurement".
@@ -127,24 +133,32 @@ def gpu_eager_reference_run(wl, sd, dev, steps=3, warmup=1):
 
 
 def run_reference_arm(args):
+    """The reference algorithm (oracle port) on the host cores, on OUR arm's config: the whole 245 760-ray stereo frame per
+    step.  A frame takes ~10 s of CPU, so the number of timed steps is capped to what fits ~2 minutes (reported)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     wl = make_workload(args)
     sd = weights_state_dict(wl)
-    n_rays = 15360                                   # 1/16 of the stereo frame per step (bounded sample)
-    sec, _ = cpu_reference_run(wl, sd, n_rays, args.steps, args.warmup)
+    n_rays = wl.rays.shape[1]
+    t0 = time.perf_counter()
+    sec_probe, _ = cpu_reference_run(wl, sd, 15360, 1, 0)               # 1/16 of the frame: how long will a frame take?
+    est = sec_probe * n_rays / 15360
+    steps = max(1, min(args.steps, int(120.0 / max(est, 1e-3))))
+    warm = 1 if (args.warmup > 0 and est < 30.0) else 0
+    sec, _ = cpu_reference_run(wl, sd, n_rays, steps, warm)
     v = n_rays / sec
     cores = torch.get_num_threads()
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "rays/s", "n_gpus": args.gpus, "steps": steps,
+            "steps_requested": args.steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded frustum, randn features in place of the encoder output)",
-            "config": {"workload": "cfg2 KITTI-360 eval_depth 192x640 K=64 stereo frame; reference algorithm on host CPU",
-                       "rays_per_step": n_rays, "samples_per_ray": K_SAMPLES},
+            "config": {"workload": "cfg2 KITTI-360 eval_depth: 192x640 stereo frame, 245760 rays/GPU, K=64, outputs rgb+depth+invalid+weights+alphas",
+                       "rays_per_gpu": n_rays, "samples_per_ray": K_SAMPLES, "impl_note": "reference algorithm (oracle port) on the host CPU; "
+                       "timed steps capped to ~2 minutes of CPU"},
             "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
-                             "sample": f"{n_rays} of the frame's 245760 rays per step, K=64, torch CPU ops chunked by 100000 points like nerf.py:244-268"},
+                             "sample": f"the whole frame ({n_rays} rays, K=64) per step, {steps} timed step(s); torch CPU ops chunked by 100000 points like nerf.py:244-268"},
             "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
     print(json.dumps(line), flush=True)
     return 0
 
@@ -232,8 +246,11 @@ def run_ours(args):
         net.encode(wl.images.to(dev), wl.Ks.to(dev), wl.poses_c2w.to(dev), ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     wants = dict(want_weights=True, want_alphas=True)
-    metric_buf = torch.zeros(2, device=dev, dtype=torch.float32)     # [sum of depths, ray count]: the per-step scalars
-    metric_buf[1] = float(n_rays)
+    # per-step scalar metric (depth sum; ray count): accumulated on the device on a side stream, all-reduced ONCE at the
+    # end -- nothing of it sits on the critical path of a step (r1: a blocking sum + clone + 8-byte NCCL all-reduce per
+    # 1.6 ms step cost 10 % at 8 GPUs)
+    metric_acc = torch.zeros(2, device=dev, dtype=torch.float64)
+    side = torch.cuda.Stream(dev)
 
     def one_step(timed, ev=None):
         flush.fill_(1)                                                 # evict L2 (126 MB) -- outside the event pair
@@ -244,15 +261,24 @@ def run_ours(args):
         if ev:
             ev[1].record()
         out = wrapped(rays_dev, **wants)["coarse"]
-        if ev:
-            ev[3].record()
-        metric_buf[0].copy_(out["depth"].sum())                        # per-rank partial of the step's scalar metric
-        red = metric_buf.clone()
-        if world > 1:
-            dist.all_reduce(red, op=dist.ReduceOp.SUM)                 # the path's only collective (NCCL, 8 bytes)
-        if ev:
-            ev[2].record()
-        return out, {"depth_sum": red[0], "rays": red[1]}
+        done = ev[2] if ev else torch.cuda.Event()
+        done.record()                                                  # end of the step on the compute stream
+        side.wait_event(done)
+        with torch.cuda.stream(side):
+            metric_acc[0] += out["depth"].sum(dtype=torch.float64)
+            metric_acc[1] += float(n_rays)
+        out["depth"].record_stream(side)
+        return out
+
+    def finish_metric():
+        """the path's only collective: SUM of the accumulated scalars (NCCL, 16 bytes), once, on the side stream"""
+        with torch.cuda.stream(side):
+            red = metric_acc.clone()
+            if world > 1:
+                dist.all_reduce(red, op=dist.ReduceOp.SUM)
+            fin = torch.cuda.Event(enable_timing=True)
+            fin.record(side)
+        return red, fin
 
     def sync_all():
         if world > 1:
@@ -292,23 +318,28 @@ def run_ours(args):
 
     with torch.no_grad():
         for _ in range(max(args.warmup, 3)):
-            out, metric = one_step(False)      # keep the results alive exactly like the timed loop does: the caching
-        sync_all()                             # allocator must reach its steady state (two output sets) before timing
-        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+            out = one_step(False)              # keep the results alive exactly like the timed loop does: the caching
+        finish_metric()                        # allocator must reach its steady state (two output sets) before timing
+        sync_all()
+        metric_acc.zero_()
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
         t_wall0 = time.perf_counter()
         for i in range(args.steps):
-            out, metric = one_step(True, evs[i])
+            out = one_step(True, evs[i])
+        metric, fin = finish_metric()
         sync_all()
         wall = time.perf_counter() - t_wall0
     prep_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
-    render_ms = sum(e[1].elapsed_time(e[3]) for e in evs) / args.steps
-    metric_ms = sum(e[3].elapsed_time(e[2]) for e in evs) / args.steps      # depth-sum + scalar all-reduce
-    per_step_render = sorted(e[1].elapsed_time(e[3]) for e in evs)
+    render_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+    # what the metric adds to the job: the part of the side-stream work that outlasts the last step
+    metric_tail_ms = max(0.0, evs[-1][2].elapsed_time(fin))
+    per_step_render = sorted(e[1].elapsed_time(e[2]) for e in evs)
     mem = torch.cuda.memory_stats(dev)
     diag = {"render_ms_min": per_step_render[0], "render_ms_median": per_step_render[len(per_step_render) // 2],
-            "render_ms_max": per_step_render[-1], "first_steps_ms": [round(e[1].elapsed_time(e[3]), 3) for e in evs[:6]],
+            "render_ms_max": per_step_render[-1], "first_steps_ms": [round(e[1].elapsed_time(e[2]), 3) for e in evs[:6]],
             "cuda_mallocs": mem.get("num_device_alloc", -1), "alloc_retries": mem.get("num_alloc_retries", -1)}
-    step_ms = sum(e[0].elapsed_time(e[2]) for e in evs) / args.steps
+    step_ms = (sum(e[0].elapsed_time(e[2]) for e in evs) + metric_tail_ms) / args.steps
+    handed = int(net._band_work[0].item()) if getattr(net, "_band_work", None) is not None else None
     kernel_name = lib.bts_last_kernel().decode()
 
     # ---- end to end through the public API with HOST buffers -----------------------------------------------------------
@@ -434,20 +465,32 @@ def run_ours(args):
         roof.update({"traffic": traffic, "kernel": f"render_{kernel_name}", "kernel_ms": kern_ms, "peak_source": pk["source"],
                      "hbm_frac": f_h, "tensor_frac": f_t, "algorithmic_bytes_per_ray": BYTES_PER_RAY,
                      "algorithmic_dense_flop_per_ray": DENSE_FLOP_PER_RAY})
+        # the unit that actually binds (neither HBM nor the tensor pipe): issue-slot and LSU-pipe utilisation of the
+        # kernel from the committed ncu capture of this command (profiles/kernel_metrics.json), not measured live
+        mp = os.path.join(ROOT, "profiles", "kernel_metrics.json")
+        if os.path.isfile(mp):
+            km = json.load(open(mp)).get(kernel_name) or {}
+            for k_src, k_dst in (("issue_slots_busy_pct", "issue_frac"), ("lsu_data_pipe_pct", "lsu_frac"), ("tensor_pipe_pct", "tensor_pipe_frac"),
+                                 ("warp_instr_per_sample", "warp_instr_per_sample"), ("source", "binding_unit_source")):
+                if k_src in km:
+                    roof[k_dst] = km[k_src] / 100.0 if k_src.endswith("_pct") else km[k_src]
         line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic (seeded KITTI-shaped frustum; randn features stand in for the encoder output, random-init MLP)",
                 "config": {"workload": "cfg2 KITTI-360 eval_depth: 192x640 stereo frame, 245760 rays/GPU, K=64, outputs rgb+depth+invalid+weights+alphas",
                            "rays_per_gpu": n_rays, "samples_per_ray": K_SAMPLES, "parallelism": f"ray-shard x{world}",
                            "l2": "256 MiB flush before every timed step", "precision_tier": "exact-fp32" if args.precision == 0 else "fast",
-                           "kernel": kernel_name, "ms_fold_pack": prep_ms, "ms_render": render_ms, "ms_metric_allreduce": metric_ms, "diag": diag},
+                           "kernel": kernel_name, "ms_fold_pack": prep_ms, "ms_render": render_ms,
+                           "ms_metric_tail": metric_tail_ms, "metric": "depth sum + ray count accumulated on a side stream, one NCCL all-reduce at the end",
+                           "band_groups_handed_to_gather_kernel": handed, "diag": diag},
                 "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": int(depth_host.numel() * 4 + rgb_host.numel() * 4), "ms_per_step": e2e_ms,
                         "how": "3-stream pipeline (H2D | fold+pack+render | D2H), every step copies its own inputs and result; steady-state period between compute starts of step 3 and step 3+steps",
                         "ms_per_step_unpipelined": e2e_seq_ms},
-                "gpu_launches": args.steps * (3 + 1),          # fold, fold_empty, pack_images, render per step (ours)
+                # ours, per step: fold, fold_empty, pack_g16, pack_images, render_band, render_tc (work-list pass)
+                "gpu_launches": args.steps * 6,
                 "roofline": roof, "clocks": clocks, "wall_s_timed_loop": wall,
-                "depth_sum_check": float(metric["depth_sum"].item())}
+                "depth_sum_check": float(metric[0].item()), "rays_check": float(metric[1].item())}
         if world == 1 and not args.no_cpu_baseline:
             # reference algorithm on this box's host cores, bounded sample, + depth abs_rel of our path vs it (same u)
             n_s = 61440
@@ -472,6 +515,42 @@ def run_ours(args):
                                          "speedup_ours_vs_it": value / (n_frame / (ms * 1e-3))}
             except Exception as e:  # baseline only: never fail the bench because of it
                 line["ref_eager_gpu"] = {"unavailable": repr(e)[:200]}
+    # ---- the other BASELINE configs + strong scaling, as extra keys of the same line -----------------------------------
+    extra = {}
+    if not args.no_extras:
+        from tools import bench_workloads as bw
+        pk = peaks()
+
+        state = {"dead": False}
+
+        def guarded(name, fn):
+            if state["dead"]:
+                extra[name] = {"skipped": "an earlier extra left the CUDA context unusable"}
+                return
+            try:
+                t0 = time.perf_counter()
+                extra[name] = fn()
+                extra[name]["wall_s"] = round(time.perf_counter() - t0, 1)
+            except Exception as e:           # an extra must never take the headline number down with it
+                extra[name] = {"failed": repr(e)[:300]}
+            try:
+                torch.cuda.synchronize(dev)
+                torch.cuda.empty_cache()
+            except Exception as e:
+                state["dead"] = True
+                extra[name] = {"failed": repr(e)[:300]}
+        with torch.no_grad():
+            net.encode(wl.images.to(dev), wl.Ks.to(dev), wl.poses_c2w.to(dev), ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
+        wrapped.renderer.precision = args.precision
+        frame_dev = frame_rays.to(dev)
+        guarded("strong_cfg2_frame", lambda: bw.strong_cfg2(net, wrapped, frame_dev, dev, min(args.steps, 50), flush))
+        del frame_dev
+        guarded("cfg3_train_step", lambda: bw.cfg3_train_step(dev, pk, steps=min(args.steps, 10), with_reference=(world == 1 and not args.no_ref_gpu)))
+        guarded("cfg4_re10k", lambda: bw.cfg4_re10k(dev, pk, steps=min(args.steps, 20)))
+        guarded("strong_cfg5_stress", lambda: bw.cfg5_stress(dev, pk, 4096 * 4096, steps=2))
+    if rank == 0:
+        if extra:
+            line["extra"] = extra
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -487,6 +566,7 @@ def main():
     ap.add_argument("--precision", type=int, default=0, help="0 exact-fp32 tier, 1 fast tier")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the eager-PyTorch-on-GPU reference leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (strong scaling, cfg3/4/5)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -9,8 +9,10 @@ from tests import parity_util as pu
 from tests.golden_io import golden_names, load_golden
 
 pytestmark = pytest.mark.gpu
-# fp32 with atomics in a different order + the ulp-level projection sensitivity: relative L2 error
-GRAD_REL_TOL = 2e-3
+# fp32 with atomics in a different order + the ulp-level projection sensitivity: relative L2 error per
+# gradient tensor.  Measured 3e-7 .. 4e-6 on B200 (r02); the bound is ~10x that, far below what a sign or term error in
+# even a small contribution would produce
+GRAD_REL_TOL = 5e-5
 
 
 def cuda_gradients(wl, sd, precision=0, use_u=True, loss_fn=gu.probe_loss):
@@ -197,4 +199,63 @@ def test_tensor_core_backward_shapes_vs_oracle_autograd(variant):
     ref = gu.oracle_gradients(wl, sd, loss_fn=loss_fn)
     errs = {k: gu.rel_err(got[k], ref[k]) for k in ref}
     print(variant, errs)
+    assert max(errs.values()) <= GRAD_REL_TOL, errs
+
+
+class _TwoScaleEncoder(torch.nn.Module):
+    """Encoder stand-in with two latents (scale 1 at half resolution), like the monodepth2 decoder's multi-scale output
+    (models/common/backbones/monodepth2.py:235-237)."""
+
+    def __init__(self, f0, f1):
+        super().__init__()
+        self.f0, self.f1 = torch.nn.Parameter(f0.clone()), torch.nn.Parameter(f1.clone())
+        self.latent_size = f0.shape[1]
+        self.scales = [0, 1]
+
+    def forward(self, x):
+        return [self.f0, self.f1]
+
+
+def test_multiscale_training_backward_uses_each_forward_scene():
+    """prediction_mode 'multiscale' (models/bts/trainer.py:220-242): every scale is rendered (set_scale + render) and ONE
+    loss.backward() follows.  Each render's backward must scatter into the folded map of ITS scale, not the last one set."""
+    import torch.nn.functional as F
+    from behindthescenes_b200 import BTSNet, NeRFRenderer
+    wl = syn.cfg3_kitti_raw_train(H=32, W=96, n=1, lin_out_bias=-4.0, seed=48, ray_subsample=512)
+    g = torch.Generator().manual_seed(5)
+    f1 = torch.randn((1, 64, 16, 48), generator=g)
+    torch.manual_seed(wl.weight_seed)
+    net = BTSNet(wl.model_conf, encoder=_TwoScaleEncoder(wl.feats, f1))
+    with torch.no_grad():
+        net.mlp_coarse.lin_out.bias.fill_(-4.0)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items() if not k.startswith("encoder.")}
+    net = net.cuda()
+    wrapped = NeRFRenderer.from_conf(wl.renderer_conf).bind_parallel(net, gpus=None).eval()
+    net.encode(wl.images.cuda(), wl.Ks.cuda(), wl.poses_c2w.cuda(), ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
+    rays, u = wl.rays.cuda(), wl.u.cuda()
+    loss = 0.0
+    for scale in (0, 1):                                   # render every scale first ...
+        net.set_scale(scale)
+        out = wrapped(rays, want_weights=True, want_alphas=True, u=u)["coarse"]
+        loss = loss + (1.0 + scale) * gu.probe_loss(out)
+    loss.backward()                                        # ... then one backward (the scene of scale 1 is current now)
+    got = {"f0": net.encoder.f0.grad.cpu(), "f1": net.encoder.f1.grad.cpu(), "w_in": net.mlp_coarse.lin_in.weight.grad.cpu(),
+           "w_out": net.mlp_coarse.lin_out.weight.grad.cpu()}
+    # autograd through the oracle, same nearest-neighbour resize of the coarser latent (models_bts.py:126)
+    f0o, f1o = wl.feats.clone().requires_grad_(True), f1.clone().requires_grad_(True)
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and not k.startswith("code_xyz")}
+    fcfg = orc_field = None
+    from oracle import bts_oracle as orc
+    from tests.golden_io import mlp_params
+    fcfg, rcfg = orc.FieldConfig.from_model_conf(wl.model_conf), orc.RenderConfig.from_renderer_conf(wl.renderer_conf)
+    total = 0.0
+    for scale, f in ((0, f0o), (1, F.interpolate(f1o, (32, 96)))):
+        st = orc.encode_state(wl.images, wl.Ks, wl.poses_c2w, f, wl.ids_encoder, wl.ids_render)
+        out = orc.render(st, mlp_params(sdo), fcfg, rcfg, wl.rays, u=wl.u, empty_feature=sdo.get("empty_feature"),
+                         want_weights=True, want_alphas=True)["coarse"]
+        total = total + (1.0 + scale) * gu.probe_loss(out)
+    total.backward()
+    want = {"f0": f0o.grad, "f1": f1o.grad, "w_in": sdo["mlp_coarse.lin_in.weight"].grad, "w_out": sdo["mlp_coarse.lin_out.weight"].grad}
+    errs = {k: gu.rel_err(got[k], want[k]) for k in want}
+    print(errs)
     assert max(errs.values()) <= GRAD_REL_TOL, errs

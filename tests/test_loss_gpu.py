@@ -4,8 +4,6 @@ the reference fixture and against the CPU oracle with torch autograd on larger s
 Tolerances: the SSIM ratio amplifies fp32 summation-order differences where the window variance is ~0 (C2 = 9e-4 is the
 only thing in the denominator), so per-ray values are compared at 2e-5 absolute (values are O(0.1)), the mean at 2e-6, the
 gradient at 1e-3 relative in the max norm."""
-import warnings
-
 import pytest
 import torch
 
@@ -123,24 +121,17 @@ def test_edge_aware_smoothness_against_oracle_autograd(shape):
     loss_o.backward()
     dev = torch.device("cuda")
     tol = 1e-5 * max(1.0, per_ray_o.max().item())
-    for attempt in range(2):
-        d = depth.to(dev).requires_grad_(True)
-        loss, per_ray = patch_edge_aware_smoothness(d, gt.to(dev), invalid_ray=invalid.to(dev))
-        loss.backward()
-        got, want = per_ray.detach().cpu(), per_ray_o.detach()
-        err = (got - want).abs()
-        if err.max().item() < tol:
-            break
+    d = depth.to(dev).requires_grad_(True)
+    loss, per_ray = patch_edge_aware_smoothness(d, gt.to(dev), invalid_ray=invalid.to(dev))
+    loss.backward()
+    got, want = per_ray.detach().cpu(), per_ray_o.detach()
+    err = (got - want).abs()
+    if err.max().item() >= tol:          # diagnostics for the r01 transient (never reproduced since: see the stability test below)
         worst = err.flatten().argmax().item()
         off = (err > tol).flatten().nonzero().flatten()
-        note = (f"attempt {attempt}: worst idx {worst} (patch {worst // (h * w)}, px {worst % (h * w)}): gpu {got.flatten()[worst].item():.7f} "
-                f"ref {want.flatten()[worst].item():.7f}; {off.numel()} elements off in patches "
-                f"{sorted(set((off // (h * w)).tolist()))[:8]}; ratio gpu/ref there {(got.flatten()[off] / want.flatten()[off]).tolist()[:8]}")
-        # Seen twice in ~25 runs of this file (never in isolation: tests/manual/debug_smooth_flake.py, 300 launches, bit-stable):
-        # a few elements of ONE launch off by ~5e-5 relative right after the render tests of this process.  The kernel has
-        # no data-dependent scheduling, so an identical relaunch tells a transient apart from a wrong result.
-        assert attempt == 0, note
-        warnings.warn("patch_smooth forward mismatch on the first launch, relaunching once: " + note)
+        pytest.fail(f"worst idx {worst} (patch {worst // (h * w)}, px {worst % (h * w)}): gpu {got.flatten()[worst].item():.7f} "
+                    f"ref {want.flatten()[worst].item():.7f}; {off.numel()} elements off in patches "
+                    f"{sorted(set((off // (h * w)).tolist()))[:8]}; ratio gpu/ref there {(got.flatten()[off] / want.flatten()[off]).tolist()[:8]}")
     assert abs(loss.item() - loss_o.item()) < 1e-5 * max(1.0, abs(loss_o.item()))
     assert _rel(d.grad.cpu(), ref.grad) < GRAD_REL or ref.grad.abs().max() == 0
 
@@ -199,3 +190,40 @@ def test_reconstruction_loss_unsupported_options_raise():
         ReconstructionLoss({"criterion": "l1+ssim"}, use_automasking=True)
     with pytest.raises(ValueError):
         ReconstructionLoss({"criterion": "l1+ssim", "alpha_reg_reduction": "patch"})
+
+
+def test_smoothness_is_bit_stable_between_render_launches():
+    """r01 saw one patch_smooth launch a few 1e-5 off right after render tests of the same process (twice in ~25 runs).
+    200 forward + backward launches interleaved with renders of both kernel families, every one compared bit for bit with
+    the first: the kernels are deterministic (compute-sanitizer memcheck / racecheck / initcheck / synccheck are clean on
+    them, profiles/r02_sanitizer_loss.md)."""
+    from oracle import loss_oracle as lo
+    from behindthescenes_b200 import synthetic as syn
+    from behindthescenes_b200.loss import patch_edge_aware_smoothness
+    dev = torch.device("cuda")
+    shape = (4, 64, 8, 8)
+    n, pc, h, w = shape
+    g = torch.Generator().manual_seed(sum(shape) + 1)
+    gt = torch.rand((n, pc, h, w, 3), generator=g)
+    depth = 2 + 90 * torch.rand(shape, generator=g)
+    depth[0, 0].fill_(7.0)
+    invalid = torch.rand(shape, generator=g) > 0.7
+    _, ref = lo.smooth_loss(depth, gt, invalid)
+    wl = syn.cfg2_kitti360_eval(H=48, W=160, stereo=True, lin_out_bias=-4.0, seed=31, ray_subsample=8000)
+    net, wrapped = syn.build_model(wl, dev)
+    with torch.no_grad():
+        net.encode(wl.images.to(dev), wl.Ks.to(dev), wl.poses_c2w.to(dev), ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
+    rays = wl.rays.to(dev)
+    first = None
+    for it in range(200):
+        with torch.no_grad():
+            wrapped.renderer.band = bool(it & 1)
+            wrapped(rays, want_weights=True, want_alphas=True)
+        d = depth.to(dev).requires_grad_(True)
+        loss, per_ray = patch_edge_aware_smoothness(d, gt.to(dev), invalid_ray=invalid.to(dev))
+        loss.backward()
+        got, grad = per_ray.detach().cpu(), d.grad.cpu()
+        if first is None:
+            first = (got.clone(), grad.clone())
+            assert (got - ref).abs().max().item() < 1e-5 * max(1.0, ref.max().item())
+        assert torch.equal(got, first[0]) and torch.equal(grad, first[1]), f"launch {it} differs from launch 0"
