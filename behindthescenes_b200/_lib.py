@@ -36,7 +36,8 @@ class BtsRenderCfg(C.Structure):
                 ("learn_empty", C.c_int32), ("num_freqs", C.c_int32), ("include_input", C.c_int32),
                 ("freq_factor", C.c_float), ("z_near", C.c_float), ("z_far", C.c_float),
                 ("inv_z_far", C.c_float), ("inv_z_range", C.c_float), ("z_range", C.c_float),
-                ("z_steps", C.c_void_p), ("step", C.c_float), ("band_mode", C.c_int32), ("precision", C.c_int32)]
+                ("z_steps", C.c_void_p), ("step", C.c_float), ("band_mode", C.c_int32), ("seed_dev", C.c_void_p),
+                ("precision", C.c_int32)]
 
 
 class BtsRenderOut(C.Structure):

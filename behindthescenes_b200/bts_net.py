@@ -41,6 +41,34 @@ def _dev_f32(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+class _ScaleList:
+    """``grid_f_features`` of the reference (a list with one (n, nv, C, H, W) map per encoder scale, models_bts.py:125-127)
+    whose nearest-neighbour resize to the scale-0 size runs when a scale is first read, not for every scale on every encode."""
+
+    def __init__(self, latents, shape):
+        self._latents, self._shape, self._maps = list(latents), tuple(shape), {}
+
+    def __len__(self):
+        return len(self._latents)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        m = self._maps.get(i)
+        if m is None:
+            l = self._latents[i]
+            n, nv, c, h, w = self._shape
+            if tuple(l.shape[-2:]) != (h, w):
+                l = F.interpolate(l, (h, w))
+            m = self._maps[i] = l.view(n, nv, c, h, w)
+        return m
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
 class BTSNet(nn.Module):
     def __init__(self, conf, encoder: nn.Module = None):
         super().__init__()
@@ -109,7 +137,9 @@ class BTSNet(nn.Module):
             latents = [torch.flip(l, dims=(-1,)) for l in latents]
         h_, w_ = latents[0].shape[-2:]
         c_l = self.encoder.latent_size
-        self.grid_f_features = [F.interpolate(l, (h_, w_)).view(n, nv, c_l, h_, w_) for l in latents]
+        # models_bts.py:125-126 resizes EVERY latent to the scale-0 size on every encode; only the scale being rendered
+        # is ever read (set_scale), so the resize happens on first access of a scale (scale 0 is already that size)
+        self.grid_f_features = _ScaleList(latents, (n, nv, c_l, h_, w_))
         self.grid_f_Ks, self.grid_f_poses_w2c, self.grid_f_combine = take(Ks, ie), take(w2c, ie), None
         self.grid_c_imgs, self.grid_c_Ks, self.grid_c_poses_w2c, self.grid_c_combine = take(colour_src, ir), take(Ks, ir), take(w2c, ir), None
         # colour views that are the encoder view itself (eval_depth: ids_render == ids_encoder): the kernels reuse the
@@ -215,6 +245,10 @@ class BTSNet(nn.Module):
             c.z_steps = steps.data_ptr()
             c.precision = int(getattr(renderer, "precision", 0))
             c.band_mode = 0 if getattr(renderer, "band", True) else 1
+            seed_t = getattr(renderer, "seed_tensor", None)      # device int64 word mixed into the jitter seed (CUDA graphs)
+            if seed_t is not None:
+                c.seed_dev = seed_t.data_ptr()
+                keep.append(seed_t)
             keep.append(steps)
         return c, keep
 
@@ -460,31 +494,25 @@ class _RenderFunction(torch.autograd.Function):
                                     None if u_d is None else u_d.data_ptr(), int(ctx.seed) & (2 ** 64 - 1),
                                     ctx.sigma.data_ptr(), C.byref(up), C.byref(pg), stream)
         _lib.check(rc, "bts_render_bwd")
-        # dense tail of the fold G = F W_F^T + b_in (two plain GEMMs)
+        # dense tail of the fold G = F W_F^T + b_in: bts_fold_features_bwd
         nb, _, _, H, W = feats.shape
-        dG2 = dG.view(nb, H * W, Hd)
         W_F = w_in.detach()[:, :Cf]
-        f2 = feats.detach().reshape(nb, Cf, H * W)
         need_df = ctx.needs_input_grad[7]
         feats_c = feats.detach()
         w_c = w_in.detach()
-        d_feats = d_WF = None
-        if feats_c.dtype == torch.float32 and feats_c.is_contiguous() and w_c.dtype == torch.float32 and w_c.stride(1) == 1:
-            d_feats = torch.empty_like(feats_c) if need_df else None
-            d_WF, d_b = d_WF_acc, d_b_acc
-            with _lib.on_device(dev):
-                rc = lib.bts_fold_features_bwd(dG.data_ptr(), feats_c.data_ptr(), nb, Cf, H, W, w_c.data_ptr(), w_c.stride(0), Hd,
-                                               d_feats.data_ptr() if need_df else None, d_WF.data_ptr(), d_b.data_ptr(), stream)
-            if rc == 0:
-                d_b_in = d_b + dge
-            elif rc == -2:          # shape outside the tensor-core fold backward: dense formulation below
-                d_feats = d_WF = None
-            else:
-                _lib.check(rc, "bts_fold_features_bwd")
-        if d_WF is None:
-            d_feats = torch.einsum("npk,kc->ncp", dG2, W_F).reshape(feats.shape) if need_df else None
-            d_WF = torch.einsum("npk,ncp->kc", dG2, f2)
-            d_b_in = dG2.sum((0, 1)) + dge
+        if feats_c.dtype != torch.float32 or not feats_c.is_contiguous():
+            feats_c = feats_c.contiguous().float()
+        if w_c.dtype != torch.float32 or w_c.stride(1) != 1:
+            w_c = w_c.contiguous().float()
+        d_feats = torch.empty_like(feats_c) if need_df else None
+        d_WF, d_b = d_WF_acc, d_b_acc
+        with _lib.on_device(dev):
+            rc = lib.bts_fold_features_bwd(dG.data_ptr(), feats_c.data_ptr(), nb, Cf, H, W, w_c.data_ptr(), w_c.stride(0), Hd,
+                                           d_feats.data_ptr() if need_df else None, d_WF.data_ptr(), d_b.data_ptr(), stream)
+        _lib.check(rc, "bts_fold_features_bwd")        # tensor-core kernel, or the CUDA-core one for odd shapes: no torch fallback
+        d_b_in = d_b + dge
+        if d_feats is not None and d_feats.dtype != feats.dtype:
+            d_feats = d_feats.to(feats.dtype)
         d_empty = None
         if empty.numel() > 0:
             d_WF = d_WF + torch.outer(dge, empty.detach())

@@ -32,6 +32,8 @@ cudaError_t launch_band(const KernelParams& p, cudaStream_t stream);
 cudaError_t launch_pack_g16(const float* G, int n, int H, int W, int Hd, void* out, int32_t* flags, cudaStream_t stream);
 int64_t g16_bytes(int n, int H, int W, int Hd);
 int band_barrier_timeouts();
+cudaError_t launch_fold_bwd_simt(const float* dG, const float* feat, int n, int C, int64_t HW, const float* w_in, int ld, int Hd,
+                                 float* d_feat, float* d_wf, float* d_b, cudaStream_t stream);
 }  // namespace bts
 
 namespace {
@@ -239,11 +241,11 @@ int bts_fold_features_bwd(const float* d_G, const float* feat_nchw, int32_t n, i
   if (!d_G || !feat_nchw || !w_in || !d_w_f || !d_b_in) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_fold_features_bwd: null pointer");
   if (n < 1 || C < 1 || H < 1 || W < 1 || Hd < 1 || ld < C) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_fold_features_bwd: bad sizes");
   const int64_t HW = (int64_t)H * W;
-  if (!bts::fold_bwd_tc_supported(d_G, feat_nchw, d_feat_or_null, C, HW, Hd))
-    return fail(BTS_ERR_UNSUPPORTED, "bts_fold_features_bwd: needs C in {32,64}, d_hidden in {32,64}, H*W %% 4 == 0 and 16-byte "
-                "aligned tensors (got C=%d, d_hidden=%d, H*W=%lld)", C, Hd, (long long)HW);
-  const cudaError_t e = bts::launch_fold_bwd_tc(d_G, feat_nchw, n, C, HW, w_in, ld, Hd, d_feat_or_null, d_w_f, d_b_in,
-                                                reinterpret_cast<cudaStream_t>(stream));
+  cudaError_t e;
+  if (bts::fold_bwd_tc_supported(d_G, feat_nchw, d_feat_or_null, C, HW, Hd))      // TMA-fed tcgen05 kernel
+    e = bts::launch_fold_bwd_tc(d_G, feat_nchw, n, C, HW, w_in, ld, Hd, d_feat_or_null, d_w_f, d_b_in, reinterpret_cast<cudaStream_t>(stream));
+  else                                                                               // any other shape: CUDA-core kernel
+    e = bts::launch_fold_bwd_simt(d_G, feat_nchw, n, C, HW, w_in, ld, Hd, d_feat_or_null, d_w_f, d_b_in, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_fold_features_bwd: %s", cudaGetErrorString(e));
   return BTS_OK;
 }

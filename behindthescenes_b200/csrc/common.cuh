@@ -50,6 +50,12 @@ __device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t ray, uint3
   return (float)(h >> 8) * (1.0f / 16777216.0f);
 }
 
+// seed of a launch: the host word, mixed with a device word when the caller keeps one (cfg.seed_dev: the jitter then
+// changes from replay to replay of a captured CUDA graph -- the caller bumps the device word inside the graph)
+__device__ __forceinline__ uint64_t jitter_seed(const KernelParams& p) {
+  return p.cfg.seed_dev ? p.seed ^ (__ldg(p.cfg.seed_dev) * 0x9E3779B97F4A7C15ull) : p.seed;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // One ray = [origin, direction, near, far] (models/common/util/util.py:244-273), either read from the caller's tensor
 // (8 lanes load, shuffle-broadcast) or generated from the camera of its pixel.  All lanes return the same values.
@@ -113,7 +119,7 @@ __device__ __forceinline__ Ray fetch_ray(const KernelParams& p, int64_t ray, int
 // ------------------------------------------------------------------------------------------------------------------
 // `near_` / `far_` are 1/near, 1/far (rounded once per ray, like the reference's `1 / near` tensors) when lindisp.
 __device__ __forceinline__ float sample_depth(const KernelParams& p, int64_t ray, int k, float near_, float far_) {
-  const float uu = p.u ? __ldg(p.u + ray * p.cfg.n_coarse + k) : hash_uniform(p.seed, (uint64_t)ray, (uint32_t)k);
+  const float uu = p.u ? __ldg(p.u + ray * p.cfg.n_coarse + k) : hash_uniform(jitter_seed(p), (uint64_t)ray, (uint32_t)k);
   const float s = __fadd_rn(__ldg(p.cfg.z_steps + k), __fmul_rn(uu, p.cfg.step));
   const float one_m = __fsub_rn(1.0f, s);
   if (p.cfg.lindisp) return __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(near_, one_m), __fmul_rn(far_, s)));

@@ -100,8 +100,8 @@ cudaError_t launch_fold(const float* feat, int n, int C, int H, int W, const flo
   const int64_t HW = (int64_t)H * W;
   // tensor-core path (TMA-fed tcgen05 GEMM, fold_tc.cu) whenever the frame qualifies; BTS_FOLD_SIMT=1 forces the
   // CUDA-core kernel (tests compare the two)
-  const char* force_simt = getenv("BTS_FOLD_SIMT");
-  if (!(force_simt && force_simt[0] == '1') && fold_tc_supported(feat, C, HW, Hd)) {
+  static const bool force_simt = [] { const char* v = getenv("BTS_FOLD_SIMT"); return v && v[0] == '1'; }();   // read once
+  if (!force_simt && fold_tc_supported(feat, C, HW, Hd)) {
     cudaError_t e = launch_fold_tc(feat, n, C, HW, w_in, ld, b_in, Hd, G, stream);
     if (e != cudaSuccess) return e;
     if (empty && g_empty) {
@@ -125,6 +125,68 @@ cudaError_t launch_fold(const float* feat, int n, int C, int H, int W, const flo
     e = cudaGetLastError();
   }
   return e;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// General CUDA-core backward of the fold (any C, d_hidden, frame size): the shapes fold_bwd_tc.cu does not take.
+//   d_feat[b, c, p] = sum_k d_G[b, p, k] W_F[k, c]          (written)
+//   d_W_F[k, c]    += sum_{b,p} d_G[b, p, k] F[b, c, p]     (accumulated),   d_b[k] += sum_{b,p} d_G[b, p, k]
+// One CTA per tile of 64 pixels: d_G tile and W_F in shared memory; thread = pixel for d_feat (coalesced along pixels),
+// thread = (k, c) pairs for the weight gradient (register partial sums over the tile, one atomic per pair and CTA).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kBwdPix = 64;
+
+__global__ void __launch_bounds__(256) fold_bwd_simt_kernel(const float* __restrict__ dG, const float* __restrict__ feat, int C, int64_t HW,
+                                                            const float* __restrict__ w_in, int ld, int Hd, float* __restrict__ d_feat,
+                                                            float* __restrict__ d_wf, float* __restrict__ d_b) {
+  extern __shared__ float sm[];
+  float* s_dg = sm;                         // [kBwdPix][Hd + 1]
+  float* s_w = s_dg + kBwdPix * (Hd + 1);   // [Hd][C]
+  float* s_f = s_w + Hd * C;                // [C][kBwdPix]
+  const int tid = threadIdx.x, b = blockIdx.y;
+  const int64_t p0 = (int64_t)blockIdx.x * kBwdPix;
+  const int valid = (int)((HW - p0) < kBwdPix ? (HW - p0) : kBwdPix);
+  for (int i = tid; i < Hd * C; i += 256) s_w[i] = __ldg(w_in + (size_t)(i / C) * ld + (i % C));
+  for (int i = tid; i < kBwdPix * Hd; i += 256) {
+    const int p = i / Hd, k = i % Hd;
+    s_dg[p * (Hd + 1) + k] = p < valid ? __ldg(dG + ((size_t)b * HW + p0 + p) * Hd + k) : 0.0f;
+  }
+  for (int i = tid; i < C * kBwdPix; i += 256) {
+    const int c = i / kBwdPix, p = i % kBwdPix;
+    s_f[i] = p < valid ? __ldg(feat + ((size_t)b * C + c) * HW + p0 + p) : 0.0f;
+  }
+  __syncthreads();
+  if (d_feat) {                             // thread = (pixel, channel quarter)
+    const int p = tid % kBwdPix, cq = tid / kBwdPix;
+    if (p < valid)
+      for (int c = cq; c < C; c += 256 / kBwdPix) {
+        float a = 0.0f;
+        for (int k = 0; k < Hd; ++k) a = fmaf(s_dg[p * (Hd + 1) + k], s_w[k * C + c], a);
+        d_feat[((size_t)b * C + c) * HW + p0 + p] = a;
+      }
+  }
+  for (int i = tid; i < Hd * C; i += 256) { // thread = (k, c) pairs
+    const int k = i / C, c = i % C;
+    float a = 0.0f;
+    for (int p = 0; p < kBwdPix; ++p) a = fmaf(s_dg[p * (Hd + 1) + k], s_f[c * kBwdPix + p], a);
+    atomicAdd(d_wf + (size_t)k * C + c, a);
+  }
+  for (int k = tid; k < Hd; k += 256) {
+    float a = 0.0f;
+    for (int p = 0; p < kBwdPix; ++p) a += s_dg[p * (Hd + 1) + k];
+    atomicAdd(d_b + k, a);
+  }
+}
+
+cudaError_t launch_fold_bwd_simt(const float* dG, const float* feat, int n, int C, int64_t HW, const float* w_in, int ld, int Hd,
+                                 float* d_feat, float* d_wf, float* d_b, cudaStream_t stream) {
+  const size_t smem = (size_t)(kBwdPix * (Hd + 1) + Hd * C + C * kBwdPix) * sizeof(float);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(fold_bwd_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((unsigned)((HW + kBwdPix - 1) / kBwdPix), (unsigned)n);
+  fold_bwd_simt_kernel<<<grid, 256, smem, stream>>>(dG, feat, C, HW, w_in, ld, Hd, d_feat, d_wf, d_b);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_pack_images(const float* img, int nv_total, int Cc, int Hc, int Wc, float* out, cudaStream_t stream) {

@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
   constexpr uint64_t kStepW = 2 * HD, kLoW = (Lt::kOffW16lo - Lt::kOffW16hi) / 16;
   const size_t copy_bytes = (size_t)H * Wo * Lt::kBlk;     // one copy of G16 (scene.n == 1)
 
+  const uint64_t seed_eff = jitter_seed(p);
   const int n_rays = (int)p.n_items;                        // < 2^31 (launcher)
   const int n_pass = (n_rays + 7) / 8;
   const int pass0 = (int)blockIdx.x * kGroups + group, pass_stride = (int)gridDim.x * kGroups;
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
     // P0 of a chunk: depth (nerf.py:103-123, rounded like the reference's separate elementwise ops), world point,
     // projection into the encoder view, depth code, bilinear taps; the warp's tap footprint is published
     auto stage_p0 = [&](int k, float& z, float& pu, float& pv_, float& pcode) -> Tap {
-      const float uu = p.u ? __ldg(p.u + (int64_t)ray * K + k) : hash_uniform(p.seed, (uint64_t)ray, (uint32_t)k);
+      const float uu = p.u ? __ldg(p.u + (int64_t)ray * K + k) : hash_uniform(seed_eff, (uint64_t)ray, (uint32_t)k);
       const float s = __fadd_rn(s_zsteps[k], __fmul_rn(uu, cfg.step));
       const float one_m = __fsub_rn(1.0f, s);
       const float zz = __fadd_rn(__fmul_rn(near_, one_m), __fmul_rn(far_, s));

@@ -302,7 +302,10 @@ class ReconstructionLoss:
                 wvec = torch.tensor([t[1] for t in live], dtype=torch.float32, device=stacked.device)
                 self._weights[key] = wvec
             loss = torch.dot(stacked, wvec)
-        host = torch.cat((stacked.detach(), loss.detach().view(1), (ratio if ratio is not None else loss.new_zeros(())).view(1))).tolist()
+        dev_vals = torch.cat((stacked.detach(), loss.detach().view(1), (ratio if ratio is not None else loss.new_zeros(())).view(1)))
+        # ``sync_scalars = False`` keeps the logged values on the device (0-d tensors; ``float(v)`` when they are wanted):
+        # no device->host transfer in the step, which is also what lets the whole step be captured in a CUDA graph
+        host = dev_vals.tolist() if getattr(self, "sync_scalars", True) else list(dev_vals.unbind(0))
         loss_dict = {k: 0.0 for k in ("loss_rgb_coarse", "loss_rgb_fine", "loss_ray_entropy", "loss_depth_reg", "loss_alpha_reg",
                                       "loss_eas", "loss_depth_smoothness")}
         i, last = 0, 0.0

@@ -101,6 +101,8 @@ typedef struct {
   float step;              /* float(1.0 / K)                              nerf.py:112    */
   int32_t band_mode;       /* 0 = use the band kernel when scene.G16 and out.scratch are given and the shape allows,
                               1 = never (gather kernel)                                                           */
+  const uint64_t* seed_dev; /* optional device word XOR-mixed into `seed` (in-kernel jitter): lets a captured CUDA graph draw
+                              new jitter on every replay -- the caller increments the word inside the graph; NULL = unused */
   int32_t precision;       /* 0 = exact tier (tensor-core kernel with two-term operand split where the config
                               allows it, else the general fp32 kernel), 1 = fast tier (single-pass tensor core),
                               2 = exact tier forced onto the general CUDA-core kernel */
@@ -217,8 +219,8 @@ int bts_query_field(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg
  * bts_render_bwd,  d_feat (n, C, H, W) = W_F^T d_G  (written; NULL when the encoder is frozen),
  * d_w_f (Hd, C) += d_G^T F  and  d_b_in (Hd) += sum d_G  (both ACCUMULATED: zero them first).  This is the lin_in part of
  * what torch autograd does in loss.backward() (utils/base_trainer.py:297; models/common/model/resnetfc.py:88,147).
- * Tensor-core path only: C in {32, 64}, Hd in {32, 64}, H*W % 4 == 0, 16-byte aligned tensors; anything else returns
- * BTS_ERR_UNSUPPORTED and the caller keeps its own dense formulation. */
+ * Tensor-core kernel for C in {32, 64}, Hd in {32, 64}, H*W % 4 == 0 and 16-byte aligned tensors; a CUDA-core kernel for
+ * every other shape. */
 int bts_fold_features_bwd(const float* d_G, const float* feat_nchw, int32_t n, int32_t C, int32_t H, int32_t W,
                           const float* w_in, int32_t ld, int32_t Hd, float* d_feat_or_null, float* d_w_f, float* d_b_in,
                           bts_stream_t stream);

@@ -179,9 +179,7 @@ def cfg3_train_step(dev, peaks, steps=10, with_reference=True):
             R.allreduce_gradients(net.mlp_coarse.parameters(), n * Rr)
         return loss
 
-    t0 = time.perf_counter()
-    ms = timed_steps(ours, dev, steps, 3)
-    host_ms = None
+    ms_eager = timed_steps(ours, dev, steps, 3)
     for _ in range(2):
         ours()
     torch.cuda.synchronize(dev)
@@ -190,10 +188,33 @@ def cfg3_train_step(dev, peaks, steps=10, with_reference=True):
         ours()
     host_ms = (time.perf_counter() - t0) * 1e3 / 5           # host time to enqueue a step (no sync inside)
     torch.cuda.synchronize(dev)
+    # the same step captured in ONE CUDA graph (fold, render, loss, both backwards; the logged scalars stay on the device;
+    # injected jitter u -- with in-kernel jitter the renderer's `seed_tensor` device word would be bumped inside the graph):
+    # the ~7 ms of Python / launch overhead of the eager step disappear; the gradient all-reduce stays outside the graph
+    crit.sync_scalars = False
+
+    def local_step():
+        net.zero_grad(set_to_none=True)
+        net.encode(imgs, Ks, poses, ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
+        out = wrapped(rays, u=u, want_weights=True, want_alphas=True, want_invalid=False, want_invalid_mass=True)["coarse"]
+        coarse = {"rgb": out["rgb"].view(n, P, 8, 8, -1, 3), "depth": out["depth"].view(n, P, 8, 8),
+                  "invalid_mass": out["invalid_mass"].view(n, P, 8, 8, -1)}
+        crit({"coarse": [coarse], "fine": [dict(coarse)], "rgb_gt": rgb_gt.view(n, P, 8, 8, 3)})[0].backward()
+
+    replay, captured = graphed(local_step, dev)
+
+    def graph_step():
+        replay()
+        if world > 1:
+            R.allreduce_gradients(net.mlp_coarse.parameters(), n * Rr)
+
+    ms_graph = timed_steps(graph_step, dev, steps, 2) if captured else None
+    crit.sync_scalars = True
+    ms = min(ms_eager, ms_graph) if ms_graph is not None else ms_eager
     res = {"what": f"cfg3 KITTI-Raw training step: {n} frames {H}x{W} x {Rr} patch rays per GPU, K=64, 2 render views, fold + render + "
                    "shipped loss (l1+ssim, weight-guided mask, edge-aware smoothness) + backward (+ gradient all-reduce); encoder excluded",
-           "rays_per_gpu": n * Rr, "ms_per_step": ms, "rays_per_s": world * n * Rr / ms * 1e3, "host_enqueue_ms": host_ms,
-           "scaling": "weak"}
+           "rays_per_gpu": n * Rr, "ms_per_step": ms, "rays_per_s": world * n * Rr / ms * 1e3, "ms_per_step_eager": ms_eager,
+           "ms_per_step_cuda_graph": ms_graph, "cuda_graph": captured, "host_enqueue_ms_eager": host_ms, "scaling": "weak"}
     # per-GPU algorithmic work of a step: the fold and its backward stream the feature maps (F read, G written; dG
     # zeroed + read, F read, dF written), the render forward / backward do the positional-code contraction per sample
     # (x3: the backward recomputes it and forms two gradient products) and move the per-ray tensors
