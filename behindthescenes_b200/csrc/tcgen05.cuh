@@ -52,8 +52,8 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
 // Unbounded-looking waits are bounded: a pipeline bug must not hang the GPU.  On expiry the kernel traps (the launch
 // fails with a CUDA error the ABI reports) instead of carrying on with unfinished data.
 __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity, int* timeout_counter) {
-  for (uint32_t i = 0; i < (1u << 20); ++i)
-    if (mbar_try_wait_hint(bar, parity, 2000u)) return;      // <= ~2 s in total
+  for (uint32_t i = 0; i < (1u << 24); ++i)
+    if (mbar_try_wait_hint(bar, parity, 128u)) return;       // short naps: a long hint oversleeps the completion
   atomicAdd(timeout_counter, 1);
   __trap();
 }

@@ -9,9 +9,11 @@ from tests import parity_util as pu
 from tests.golden_io import golden_names, load_golden
 
 pytestmark = pytest.mark.gpu
-# fp32 with atomics in a different order + the ulp-level projection sensitivity: relative L2 error per
-# gradient tensor.  Measured 3e-7 .. 4e-6 on B200 (r02); the bound is ~10x that, far below what a sign or term error in
-# even a small contribution would produce
+# Relative L2 error per gradient tensor.  Well-conditioned workloads measure 3e-7 .. 4e-6 on B200 (r02) and are held to
+# 5e-5 -- far below what a sign or term error in even a small contribution would produce.  Where the fp32 reference gradient
+# itself is ill conditioned (ReLU-mask / frustum-flag flips of single samples under ulp-level forward differences; linear
+# depth sampling from z_near = 0.5), the bound is 4x the measured distance between the fp32 and the float64 evaluation of
+# the reference (tests/grad_util.py::grad_tolerances) -- two correct fp32 evaluations cannot agree better than that.
 GRAD_REL_TOL = 5e-5
 
 
@@ -137,10 +139,9 @@ def test_backward_option_coverage_vs_oracle_autograd(variant):
     sd = {k: v.clone() for k, v in cpu_net.state_dict().items() if not k.startswith("encoder.")}
     got, _ = cuda_gradients(wl, sd, precision=prec)
     ref = gu.oracle_gradients(wl, sd)
-    tol = GRAD_REL_TOL
-    if edge:   # flag membership of single knife-edge samples also moves d_empty: floor of 1e-3 for this workload
-        tol = gu.grad_tolerances(ref, gu.oracle_gradients64(wl, sd), 1e-3)
-    print(variant, gu.assert_grads_close(got, ref, tol, variant))
+    # flag membership of single knife-edge samples also moves d_empty in the edge workload: floor of 1e-3 there
+    tol = gu.grad_tolerances(ref, gu.oracle_gradients64(wl, sd), 1e-3 if edge else GRAD_REL_TOL)
+    print(variant, gu.assert_grads_close(got, ref, tol, variant), "bounds", tol)
 
 
 def test_backward_with_masked_rays_vs_oracle_autograd():
