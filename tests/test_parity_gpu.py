@@ -275,3 +275,43 @@ def test_batched_scene_n16_patch_rays():
     """Training-shaped batch: n=16 scenes in one launch (per-ray batch index), 2 colour views."""
     wl = syn.cfg3_kitti_raw_train(H=24, W=80, n=16, lin_out_bias=-4.0, seed=72, ray_subsample=512)
     print(_full_size_case(wl, dict(want_weights=True, want_alphas=True, want_rgb_samps=True), -4.0))
+
+
+def test_cfg4_full_size_vs_oracle():
+    """BASELINE config 4 at its full size: RealEstate10K shape 256x384 (98 304 rays of a novel view), K=128, C=32,
+    d_hidden=32 + one ResnetFC block, distance code, 2 colour views."""
+    wl = syn.cfg4_re10k_nvs(H=256, W=384, K=128, lin_out_bias=-4.0, seed=17)
+    print(_full_size_case(wl, dict(want_weights=True, want_alphas=True), -4.0))
+    assert _last_kernel() == "general"
+
+
+def test_cfg5_slice_one_million_rays():
+    """BASELINE config 5 (stress: K=256, d_hidden=128, random rays) on a 2^20-ray slice: size-independent properties on
+    every ray (weights sum to 1 under the alpha cap, sorted samples inside [near, far], depth in range, finite colours) and
+    the oracle on a 2048-ray subset of the same launch (in-kernel jitter: z_samps of the launch are fed to the oracle)."""
+    wl = syn.cfg5_stress(R=1 << 20, K=256, d_hidden=128, seed=5)
+    sd_net, _ = syn.build_model(wl, "cpu")
+    sd = {k: v.clone() for k, v in sd_net.state_dict().items() if not k.startswith("encoder.")}
+    net, wrapped = syn.build_model(wl, "cuda", state_dict=sd)
+    with torch.no_grad():
+        net.encode(wl.images.cuda(), wl.Ks.cuda(), wl.poses_c2w.cuda(), ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
+        rays = wl.rays.cuda()
+        out = wrapped(rays, want_weights=True, want_z_samps=True, want_invalid=False)["coarse"]
+    assert _last_kernel() == "tc"
+    z, w, d = out["z_samps"], out["weights"], out["depth"]
+    assert torch.isfinite(out["rgb"]).all() and torch.isfinite(d).all()
+    assert (z[..., 1:] > z[..., :-1]).all() and (z >= 3.0 - 1e-4).all() and (z <= 80.0 + 1e-3).all()
+    assert (w >= 0).all() and (w.sum(-1) - 1).abs().max().item() <= 5e-5
+    assert ((d >= 3.0 - 1e-3) & (d <= 80.0 + 1e-2)).all()
+    # oracle on a subset, with the jitter of this launch recovered from its depths (u is what maps bin k to z)
+    n_s = 2048
+    sub = syn.Workload(**{**wl.__dict__, "rays": wl.rays[:, :n_s].contiguous()})
+    disp = 1.0 / z[0, :n_s].cpu().double()
+    lo, hi = 1.0 / 80.0, 1.0 / 3.0
+    s = (hi - disp) / (hi - lo)                                   # nerf.py:117-120 inverted: s = z_steps + u / K
+    sub.u = ((s - torch.arange(256, dtype=torch.float64) / 256) * 256).clamp(0, 1).float()
+    with torch.no_grad():
+        got = wrapped(rays[:, :n_s].contiguous(), u=sub.u.cuda(), want_weights=True)["coarse"]
+    got = {k: v.cpu() for k, v in got.items()}
+    ref = pu.oracle_render(sub, sd, want_weights=True)
+    print(pu.compare_render(sub, got, ref, label="cfg5 slice"))
