@@ -32,13 +32,18 @@ namespace tcr {
 
 constexpr int kThreads = 128;
 
-// Per-width layout: TMEM columns [D: HD][A16hi: 24][A16lo: 24][Araw: 8], shared-memory map (bytes).
-template <int HD>
+// Per-shape layout: TMEM columns [D: HD][A: code operand hi 24 | lo 24 | raw 8; reused as the ResnetFC block operand hi HD/2 |
+// lo HD/2], shared-memory map (bytes).  NB = number of ResnetFC blocks run on the tensor cores (0 | 1).
+template <int HD, int NB>
 struct L {
-  static_assert(HD == 64 || HD == 128, "tensor-core kernel: d_hidden 64 or 128");
+  static_assert(HD == 32 || HD == 64 || HD == 128, "tensor-core kernel: d_hidden 32, 64 or 128");
+  static_assert(NB == 0 || (NB == 1 && HD <= 64), "ResnetFC block on the tensor cores: one block, d_hidden <= 64");
   static constexpr uint32_t kColD = 0, kColAhi = HD, kColAlo = HD + 24, kColAraw = HD + 48;
-  static constexpr uint32_t kTmemCols = HD == 64 ? 128 : 256;
-  static constexpr int kCtasPerSm = HD == 64 ? 4 : 2;          // 512 TMEM columns per SM
+  static constexpr uint32_t kColBhi = HD, kColBlo = HD + HD / 2;            // block operand (relu'd activations, fp16 hi / lo)
+  static constexpr uint32_t kColsUsed = HD + (NB && HD > 56 ? HD : 56);
+  static constexpr uint32_t kTmemCols = kColsUsed <= 128 ? 128 : 256;
+  // 512 TMEM columns per SM; the 64-wide block variant keeps 64 activations per thread in registers -> 2 CTAs (255 registers)
+  static constexpr int kCtasPerSm = (HD == 128 || (HD == 64 && NB == 1)) ? 2 : 4;
   static constexpr int kLanesPerSample = HD / 4;               // one float4 (4 channels) per lane in the gather
   static constexpr int kSamplesPerIter = 32 / kLanesPerSample;
   static constexpr int kGiStride = HD + 4;                     // floats per interpolated row (+4: conflict-free both ways)
@@ -48,7 +53,10 @@ struct L {
   static constexpr int kOffWrawB = kOffWrawA + 2 * HD * 16;    //               tf32: [lo0 lo1 lo2 0 | 0 0 0 0]
   static constexpr int kOffWout = kOffWrawB + 2 * HD * 16;     // HD floats
   static constexpr int kOffGempty = kOffWout + HD * 4;         // HD floats
-  static constexpr int kOffBar = kOffGempty + HD * 4;          // mbarrier (8 B) + tmem base (4 B) + pad
+  static constexpr int kBlkPlane = 2 * HD * HD;                // one fp16 plane of a HD x HD block matrix: [HD/8 chunks][HD rows][16 B]
+  static constexpr int kOffBlk = kOffGempty + HD * 4;          // [fc_0 | fc_1][hi | lo] planes, then the two bias vectors
+  static constexpr int kOffBlkBias = kOffBlk + NB * 4 * kBlkPlane;
+  static constexpr int kOffBar = kOffBlkBias + NB * 2 * HD * 4;   // mbarrier (8 B) + tmem base (4 B) + pad
   static constexpr int kOffWarp = kOffBar + 16;
   static constexpr int kWarpTaps = 0;                          // [32][8] floats
   static constexpr int kWarpGi = 32 * 8 * 4;                   // [32][HD + 4] floats
@@ -73,9 +81,12 @@ __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__flo
 
 // kPoints: point-query entry (BTSNet.forward on explicit xyz, models_bts.py:266-338): a pass is 128 points (lane = point),
 // the same P1/MMA/P2/P3, no compositing.
-template <int HD, bool kExact, bool kPoints>
-__global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_tc_kernel(const KernelParams p) {
-  using Lt = L<HD>;
+// NB = 1: one ResnetFC block (models/common/model/resnetfc.py:53-62: h + fc_1(relu(fc_0(relu(h))))) as two more MMA rounds
+// on the accumulator: relu'd activations -> fp16 hi/lo -> TMEM operand (the code operand's columns) -> D; the RealEstate10K
+// field (configs/exp_re10k.yaml:43-44: d_hidden 32, n_blocks 1).
+template <int HD, bool kExact, bool kPoints, int NB>
+__global__ void __launch_bounds__(kThreads, L<HD, NB>::kCtasPerSm) render_tc_kernel(const KernelParams p) {
+  using Lt = L<HD, NB>;
   constexpr uint32_t kColD = Lt::kColD, kColAhi = Lt::kColAhi, kColAlo = Lt::kColAlo, kColAraw = Lt::kColAraw, kTmemCols = Lt::kTmemCols;
   constexpr int kOffW16hi = Lt::kOffW16hi, kOffW16lo = Lt::kOffW16lo, kOffWrawA = Lt::kOffWrawA, kOffWrawB = Lt::kOffWrawB;
   constexpr int kOffWout = Lt::kOffWout, kOffGempty = Lt::kOffGempty, kOffBar = Lt::kOffBar, kOffWarp = Lt::kOffWarp;
@@ -127,6 +138,19 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_tc_kernel(
     s_wout[n] = __ldg(p.mlp.w_out + n);
     s_gempty[n] = p.scene.g_empty ? __ldg(p.scene.g_empty + n) : 0.0f;
   }
+  if constexpr (NB == 1) {   // fc_0 / fc_1 (nn.Linear weight [out][in]) as B operands: row n = output unit, K index = input unit
+    for (int i = tid; i < 2 * HD * HD; i += kThreads) {
+      const int m = i / (HD * HD), n = (i / HD) % HD, c = i % HD;
+      const float w = __ldg((m == 0 ? p.mlp.fc0_w[0] : p.mlp.fc1_w[0]) + (size_t)n * HD + c);
+      const __half hi = __float2half_rn(w);
+      const __half lo = __float2half_rn(w - __half2float(hi));
+      const int off = ((c >> 3) * HD + n) * 16 + (c & 7) * 2;
+      *reinterpret_cast<__half*>(smem + Lt::kOffBlk + (2 * m + 0) * Lt::kBlkPlane + off) = hi;
+      *reinterpret_cast<__half*>(smem + Lt::kOffBlk + (2 * m + 1) * Lt::kBlkPlane + off) = lo;
+    }
+    for (int i = tid; i < 2 * HD; i += kThreads)
+      reinterpret_cast<float*>(smem + Lt::kOffBlkBias)[i] = __ldg((i < HD ? p.mlp.fc0_b[0] : p.mlp.fc1_b[0]) + (i % HD));
+  }
   if (warp == 0) tc::tmem_alloc<kTmemCols>(tmem_slot);
   if (tid == 0) {
     tc::mbar_init(bar, 1);
@@ -140,7 +164,7 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_tc_kernel(
   const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes
   uint32_t bar_phase = 0;
 
-  const int K = cfg.n_coarse, Vc = p.scene.Vc;
+  const int K = cfg.n_coarse;
   const int H = p.scene.H, W = p.scene.W;
   const float b_out = __ldg(p.mlp.b_out);
   const bool use_empty = cfg.learn_empty && p.scene.g_empty != nullptr;
@@ -186,16 +210,18 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_tc_kernel(
     for (int i = lane; i < kMaxColorViews * 5; i += 32) w_rgb[i] = 0.0f;
     if (p.scene.n != 1) load_view(vf, p.scene.K_f + b * 9, p.scene.w2c_f + b * 16);
 
-    float z_ahead = kPoints ? 0.0f : sample_depth(p, ray, lane, near_, far_);   // depths are produced one chunk ahead
+    float z_ahead = kPoints ? 0.0f : sample_depth(p, ray, (lane < K ? lane : K - 1), near_, far_);   // depths are produced one chunk ahead
     const int Kloop = kPoints ? 32 : K;
     for (int c0 = 0; c0 < Kloop; c0 += 32) {
-      const int k = c0 + lane;
+      const int k_raw = c0 + lane;
+      const bool in_k = kPoints || k_raw < K;            // ragged last chunk (K % 32 != 0): lanes past K idle along
+      const int k = in_k ? k_raw : K - 1;
       const int64_t sample_id = kPoints ? ray : ray * K + k;
       // ---------------- P1: per-sample scalar work, A operand -> TMEM ----------------
       float z = 0.0f, z_next = 0.0f, X, Y, Z;
       if constexpr (!kPoints) {
         z = z_ahead;
-        z_ahead = (c0 + 32 < K) ? sample_depth(p, ray, k + 32, near_, far_) : 0.0f;
+        z_ahead = (c0 + 32 < K) ? sample_depth(p, ray, (k_raw + 32 < K ? k_raw + 32 : K - 1), near_, far_) : 0.0f;
         z_next = __shfl_down_sync(0xffffffffu, z, 1);
         const float z_first_of_next = __shfl_sync(0xffffffffu, z_ahead, 0);
         if (lane == 31) z_next = z_first_of_next;
@@ -378,49 +404,158 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_tc_kernel(
       bar_phase ^= 1u;
       tc::tc_fence_after_sync();
       float logit = b_out;
-#pragma unroll
-      for (int grp = 0; grp < HD / 64; ++grp) {      // 64 accumulator columns at a time (register budget)
-        uint32_t dv[4][16];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tc::tmem_ld_x16(t_lane + kColD + grp * 64 + c * 16, dv[c]);
-        tc::tmem_ld_wait();
-        const float4* grow = reinterpret_cast<const float4*>(w_gi + lane * kGiStride + grp * 64);
-        const float4* wo4 = reinterpret_cast<const float4*>(s_wout + grp * 64);
-        if (!big) {
-          float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;   // four independent chains (ILP)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float4 g = grow[c * 4 + e];
-              const float4 wv = wo4[c * 4 + e];
-              l0 = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 0]) + g.x, 0.0f), wv.x, l0);
-              l1 = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 1]) + g.y, 0.0f), wv.y, l1);
-              l2 = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 2]) + g.z, 0.0f), wv.z, l2);
-              l3 = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 3]) + g.w, 0.0f), wv.w, l3);
+      if constexpr (NB == 0 && HD >= 64) {
+  #pragma unroll
+        for (int grp = 0; grp < HD / 64; ++grp) {      // 64 accumulator columns at a time (register budget)
+          uint32_t dv[4][16];
+  #pragma unroll
+          for (int c = 0; c < 4; ++c) tc::tmem_ld_x16(t_lane + kColD + grp * 64 + c * 16, dv[c]);
+          tc::tmem_ld_wait();
+          const float4* grow = reinterpret_cast<const float4*>(w_gi + lane * kGiStride + grp * 64);
+          const float4* wo4 = reinterpret_cast<const float4*>(s_wout + grp * 64);
+          if (!big) {
+            float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;   // four independent chains (ILP)
+  #pragma unroll
+            for (int c = 0; c < 4; ++c) {
+  #pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float4 g = grow[c * 4 + e];
+                const float4 wv = wo4[c * 4 + e];
+                l0 = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 0]) + g.x, 0.0f), wv.x, l0);
+                l1 = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 1]) + g.y, 0.0f), wv.y, l1);
+                l2 = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 2]) + g.z, 0.0f), wv.z, l2);
+                l3 = fmaf(fmaxf(__uint_as_float(dv[c][e * 4 + 3]) + g.w, 0.0f), wv.w, l3);
+              }
             }
-          }
-          logit += (l0 + l1) + (l2 + l3);
-        } else {   // rare: raw-coordinate part of lin_in in fp32
-          const float4* wrh = reinterpret_cast<const float4*>(smem + kOffWrawA) + grp * 64;   // chunk 0: [hi0 hi1 hi2 hi0]
-          const float4* wrl = reinterpret_cast<const float4*>(smem + kOffWrawB) + grp * 64;   // chunk 0: [lo0 lo1 lo2 0]; hi+lo = fp32 weight
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float4 g = grow[c * 4 + e];
-              const float4 wv = wo4[c * 4 + e];
-              const float gv[4] = {g.x, g.y, g.z, g.w}, wo[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float4 wh = wrh[c * 16 + e * 4 + t], wl = wrl[c * 16 + e * 4 + t];
-                float h = __uint_as_float(dv[c][e * 4 + t]) + gv[t];
-                h = fmaf(wh.z + wl.z, pv[2], fmaf(wh.y + wl.y, pv[1], fmaf(wh.x + wl.x, pv[0], h)));
-                logit = fmaf(fmaxf(h, 0.0f), wo[t], logit);
+            logit += (l0 + l1) + (l2 + l3);
+          } else {   // rare: raw-coordinate part of lin_in in fp32
+            const float4* wrh = reinterpret_cast<const float4*>(smem + kOffWrawA) + grp * 64;   // chunk 0: [hi0 hi1 hi2 hi0]
+            const float4* wrl = reinterpret_cast<const float4*>(smem + kOffWrawB) + grp * 64;   // chunk 0: [lo0 lo1 lo2 0]; hi+lo = fp32 weight
+  #pragma unroll
+            for (int c = 0; c < 4; ++c) {
+  #pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float4 g = grow[c * 4 + e];
+                const float4 wv = wo4[c * 4 + e];
+                const float gv[4] = {g.x, g.y, g.z, g.w}, wo[4] = {wv.x, wv.y, wv.z, wv.w};
+  #pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float4 wh = wrh[c * 16 + e * 4 + t], wl = wrl[c * 16 + e * 4 + t];
+                  float h = __uint_as_float(dv[c][e * 4 + t]) + gv[t];
+                  h = fmaf(wh.z + wl.z, pv[2], fmaf(wh.y + wl.y, pv[1], fmaf(wh.x + wl.x, pv[0], h)));
+                  logit = fmaf(fmaxf(h, 0.0f), wo[t], logit);
+                }
               }
             }
           }
         }
+      } else {
+        // d_hidden 32 and / or one ResnetFC block: the whole pre-activation row in registers
+        float h[HD];
+        {
+          const float4* wrh = reinterpret_cast<const float4*>(smem + kOffWrawA);   // chunk 0: [hi0 hi1 hi2 hi0]
+          const float4* wrl = reinterpret_cast<const float4*>(smem + kOffWrawB);   // chunk 0: [lo0 lo1 lo2 0]
+#pragma unroll
+          for (int c = 0; c < HD / 16; ++c) {
+            uint32_t dv[16];
+            tc::tmem_ld_x16(t_lane + kColD + c * 16, dv);
+            tc::tmem_ld_wait();
+            const float4* grow = reinterpret_cast<const float4*>(w_gi + lane * kGiStride + c * 16);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float4 g = grow[e];
+              h[c * 16 + e * 4 + 0] = __uint_as_float(dv[e * 4 + 0]) + g.x;
+              h[c * 16 + e * 4 + 1] = __uint_as_float(dv[e * 4 + 1]) + g.y;
+              h[c * 16 + e * 4 + 2] = __uint_as_float(dv[e * 4 + 2]) + g.z;
+              h[c * 16 + e * 4 + 3] = __uint_as_float(dv[e * 4 + 3]) + g.w;
+            }
+            if (big) {   // rare: raw-coordinate part of lin_in in fp32
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const float4 wh = wrh[c * 16 + e], wl = wrl[c * 16 + e];
+                h[c * 16 + e] = fmaf(wh.z + wl.z, pv[2], fmaf(wh.y + wl.y, pv[1], fmaf(wh.x + wl.x, pv[0], h[c * 16 + e])));
+              }
+            }
+          }
+        }
+        if constexpr (NB == 1) {
+          const float* s_bias = reinterpret_cast<const float*>(smem + Lt::kOffBlkBias);
+          const uint32_t idesc_blk = tc::instr_desc(tc::kFmtF16, 128, HD);
+          // x -> relu(x) as fp16 hi/lo pairs -> the block operand in TMEM (over the code operand: its MMAs are complete)
+          auto put_operand = [&](const float (&x)[HD]) {
+#pragma unroll
+            for (int g = 0; g < HD / 16; ++g) {
+              uint32_t vh[8], vl[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float a0 = fmaxf(x[g * 16 + 2 * e], 0.0f), a1 = fmaxf(x[g * 16 + 2 * e + 1], 0.0f);
+                vl[e] = 0u;
+                if (kExact) split_h2(a0, a1, vh[e], vl[e]);
+                else vh[e] = pack_h2(a0, a1);
+              }
+              tc::tmem_st_x8(t_lane + Lt::kColBhi + g * 8, vh);
+              if (kExact) tc::tmem_st_x8(t_lane + Lt::kColBlo + g * 8, vl);
+            }
+            tc::tmem_st_wait();
+          };
+          // D[128 x HD] = operand x W^T of block matrix m (0: fc_0, 1: fc_1); every thread has finished with D before
+          auto block_mma = [&](int m) {
+            tc::tc_fence_before_sync();
+            __syncthreads();
+            if (tid == 0) {
+              tc::tc_fence_after_sync();
+              const uint32_t sB = tc::smem_u32(smem) + Lt::kOffBlk + 2 * m * Lt::kBlkPlane;
+#pragma unroll
+              for (int ks = 0; ks < HD / 16; ++ks) {
+                const uint64_t bhi = tc::smem_desc_kmajor_noswizzle(sB + ks * 2 * HD * 16, HD * 16, 128);
+                tc::mma_f16_ts(tmem + kColD, tmem + Lt::kColBhi + ks * 8, bhi, idesc_blk, ks > 0);
+                if (kExact) {
+                  const uint64_t blo = tc::smem_desc_kmajor_noswizzle(sB + Lt::kBlkPlane + ks * 2 * HD * 16, HD * 16, 128);
+                  tc::mma_f16_ts(tmem + kColD, tmem + Lt::kColBlo + ks * 8, bhi, idesc_blk, 1);
+                  tc::mma_f16_ts(tmem + kColD, tmem + Lt::kColBhi + ks * 8, blo, idesc_blk, 1);
+                }
+              }
+              tc::mma_commit(bar);
+            }
+            __syncwarp();
+            tc::mbar_wait_or_trap(bar, bar_phase, &g_tc_barrier_timeouts);
+            bar_phase ^= 1u;
+            tc::tc_fence_after_sync();
+          };
+          put_operand(h);
+          block_mma(0);                              // net = fc_0(relu(h))
+          {
+            float t[HD];
+#pragma unroll
+            for (int c = 0; c < HD / 16; ++c) {
+              uint32_t dv[16];
+              tc::tmem_ld_x16(t_lane + kColD + c * 16, dv);
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 16; ++e) t[c * 16 + e] = __uint_as_float(dv[e]) + s_bias[c * 16 + e];
+            }
+            put_operand(t);
+          }
+          block_mma(1);                              // dx = fc_1(relu(net))
+#pragma unroll
+          for (int c = 0; c < HD / 16; ++c) {
+            uint32_t dv[16];
+            tc::tmem_ld_x16(t_lane + kColD + c * 16, dv);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) h[c * 16 + e] += __uint_as_float(dv[e]) + s_bias[HD + c * 16 + e];   // h + dx (identity shortcut)
+          }
+        }
+        float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < HD; j += 4) {
+          const float4 wv = *reinterpret_cast<const float4*>(s_wout + j);
+          l0 = fmaf(fmaxf(h[j + 0], 0.0f), wv.x, l0);
+          l1 = fmaf(fmaxf(h[j + 1], 0.0f), wv.y, l1);
+          l2 = fmaf(fmaxf(h[j + 2], 0.0f), wv.z, l2);
+          l3 = fmaf(fmaxf(h[j + 3], 0.0f), wv.w, l3);
+        }
+        logit += (l0 + l1) + (l2 + l3);
       }
       tc::tc_fence_before_sync();          // my TMEM reads are ordered before the next tile's barrier / MMA
       const float sigma = softplus(logit);
@@ -428,8 +563,9 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_tc_kernel(
 
       // ---------------- C, D ----------------
       if constexpr (!kPoints) {
-        const float wgt = composite_chunk(p, lane, k, K, active, z, z_next, sigma, sample_id, T_carry, depth_part, wsum_part);
-        colour_views<false>(p, lane, b, X, Y, Z, active, pf, wgt, sample_id, w_rgb);
+        const bool valid = active && in_k;
+        const float wgt = composite_chunk(p, lane, k_raw, K, valid, z, z_next, sigma, sample_id, T_carry, depth_part, wsum_part);
+        colour_views<false>(p, lane, b, X, Y, Z, valid, pf, wgt, sample_id, w_rgb);
       } else {
         if (active) {
           p.q_sigma[sample_id] = sigma;
@@ -455,24 +591,31 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_tc_kernel(
 bool tc_supported(const KernelParams& p) {
   const BtsRenderCfg& c = p.cfg;
   const int64_t pixels = (int64_t)p.scene.n * p.scene.H * p.scene.W;
-  return (p.mlp.Hd == 64 || p.mlp.Hd == 128) && p.mlp.n_blocks == 0 && p.mlp.P == 39 && c.num_freqs == 6 &&
-         c.include_input && (p.xyz != nullptr || c.n_coarse % 32 == 0) && p.scene.Vc <= kMaxColorViews &&
+  const bool shape = (p.mlp.n_blocks == 0 && (p.mlp.Hd == 32 || p.mlp.Hd == 64 || p.mlp.Hd == 128)) ||
+                     (p.mlp.n_blocks == 1 && (p.mlp.Hd == 32 || p.mlp.Hd == 64));
+  return shape && p.mlp.P == 39 && c.num_freqs == 6 && c.include_input && c.n_coarse >= 1 && p.scene.Vc <= kMaxColorViews &&
          pixels * (p.mlp.Hd / 4) < (int64_t)0x7fffffff;   // tap offsets are 32-bit (float4 units)
 }
 
-template <int HD, bool kExact, bool kPoints>
+template <int HD, bool kExact, bool kPoints, int NB>
 static cudaError_t launch_tc_t(const KernelParams& p, cudaStream_t stream) {
-  using Lt = tcr::L<HD>;
-  auto kern = tcr::render_tc_kernel<HD, kExact, kPoints>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Lt::kSmemBytes);
-  if (e != cudaSuccess) return e;
-  // kCtasPerSm CTAs/SM by design (registers, shared memory, TMEM columns): ask for the full shared-memory carve-out,
-  // otherwise the default split leaves room for a single CTA.
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (e != cudaSuccess) return e;
-  int dev = 0, sms = 148;
+  using Lt = tcr::L<HD, NB>;
+  auto kern = tcr::render_tc_kernel<HD, kExact, kPoints, NB>;
+  static bool configured[64] = {};
+  static int sm_count[64] = {};
+  int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (dev < 64 && !configured[dev]) {   // once per device: function attributes and the SM count
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Lt::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    // kCtasPerSm CTAs/SM by design (registers, shared memory, TMEM columns): ask for the full shared-memory carve-out,
+    // otherwise the default split leaves room for a single CTA.
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+    configured[dev] = true;
+  }
+  const int sms = dev < 64 && sm_count[dev] > 0 ? sm_count[dev] : 148;
   const int64_t n_pass = kPoints ? (p.n_items + 127) / 128 : (p.n_items + 3) / 4;   // work-list mode: upper bound
   const int64_t cap = (int64_t)sms * Lt::kCtasPerSm;      // persistent: every CTA resident, strided over passes
   const int grid = (int)(n_pass < cap ? n_pass : cap);
@@ -480,13 +623,18 @@ static cudaError_t launch_tc_t(const KernelParams& p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_tc(const KernelParams& p, bool points, cudaStream_t stream) {
+template <int HD, int NB>
+static cudaError_t launch_tc_hd(const KernelParams& p, bool points, cudaStream_t stream) {
   const bool exact = p.cfg.precision == 0;
-  if (points) {   // query: exact tier only (it feeds occupancy thresholds / BEV profiles)
-    return p.mlp.Hd == 64 ? launch_tc_t<64, true, true>(p, stream) : launch_tc_t<128, true, true>(p, stream);
-  }
-  if (p.mlp.Hd == 64) return exact ? launch_tc_t<64, true, false>(p, stream) : launch_tc_t<64, false, false>(p, stream);
-  return exact ? launch_tc_t<128, true, false>(p, stream) : launch_tc_t<128, false, false>(p, stream);
+  if (points) return launch_tc_t<HD, true, true, NB>(p, stream);   // query: exact tier only (occupancy thresholds / BEV profiles)
+  return exact ? launch_tc_t<HD, true, false, NB>(p, stream) : launch_tc_t<HD, false, false, NB>(p, stream);
+}
+
+cudaError_t launch_tc(const KernelParams& p, bool points, cudaStream_t stream) {
+  if (p.mlp.n_blocks == 1) return p.mlp.Hd == 32 ? launch_tc_hd<32, 1>(p, points, stream) : launch_tc_hd<64, 1>(p, points, stream);
+  if (p.mlp.Hd == 32) return launch_tc_hd<32, 0>(p, points, stream);
+  if (p.mlp.Hd == 64) return launch_tc_hd<64, 0>(p, points, stream);
+  return launch_tc_hd<128, 0>(p, points, stream);
 }
 
 int tc_barrier_timeouts() {

@@ -109,10 +109,26 @@ def test_fold_backward_matches_fp64(n, C, Hd, H, W):
     assert ((d_wf2 - d_wf).abs().double() <= 1e-6 * mag_wf + 1e-30).all()
 
 
-def test_fold_backward_unsupported_shapes_are_reported():
-    feat = torch.randn((1, 48, 8, 8)).cuda()
-    rc, *_ = _fold_bwd(torch.randn((1, 8, 8, 64)).cuda(), feat, torch.randn((64, 48 + 39)).cuda(), 64)
-    assert rc == -2 and b"bts_fold_features_bwd" in _lib.load().bts_last_error()
+@pytest.mark.parametrize("n,C,Hd,H,W", [(1, 48, 64, 8, 8), (2, 64, 96, 7, 9), (1, 16, 32, 5, 13)])
+def test_fold_backward_other_shapes_take_the_cuda_core_kernel(n, C, Hd, H, W):
+    """Shapes outside the tensor-core fold backward (C not in {32, 64}, d_hidden 96, H*W % 4 != 0) run the CUDA-core kernel
+    of fold.cu -- there is no torch fallback in the autograd node any more; same fp64 yardstick."""
+    g = torch.Generator().manual_seed(n + C + Hd + H + W)
+    feat = torch.randn((n, C, H, W), generator=g).cuda()
+    w_in = torch.randn((Hd, C + 39), generator=g).cuda()
+    dG = torch.randn((n, H, W, Hd), generator=g).cuda()
+    rc, d_feat, d_wf, d_b = _fold_bwd(dG, feat, w_in, Hd)
+    assert rc == 0, _lib.load().bts_last_error()
+    W_F = w_in[:, :C].double()
+    ref_df = torch.einsum("nhwk,kc->nchw", dG.double(), W_F)
+    ref_wf = torch.einsum("nhwk,nchw->kc", dG.double(), feat.double())
+    ref_b = dG.double().sum((0, 1, 2))
+    assert (d_feat.double() - ref_df).abs().max().item() <= 3e-6 * ref_df.abs().max().item()
+    mag_wf = torch.einsum("nhwk,nchw->kc", dG.abs().double(), feat.abs().double())
+    assert ((d_wf.double() - ref_wf).abs() <= 2e-6 * mag_wf + 1e-30).all()
+    assert ((d_b.double() - ref_b).abs() <= 2e-6 * dG.abs().double().sum((0, 1, 2)) + 1e-30).all()
+    rc2, none, d_wf2, _ = _fold_bwd(dG, feat, w_in, Hd, want_df=False)
+    assert rc2 == 0 and none is None and ((d_wf2 - d_wf).abs().double() <= 1e-6 * mag_wf + 1e-30).all()
 
 
 def test_row_copy_loads_agree_with_tensor_map_loads(monkeypatch):

@@ -282,7 +282,7 @@ def test_cfg4_full_size_vs_oracle():
     d_hidden=32 + one ResnetFC block, distance code, 2 colour views."""
     wl = syn.cfg4_re10k_nvs(H=256, W=384, K=128, lin_out_bias=-4.0, seed=17)
     print(_full_size_case(wl, dict(want_weights=True, want_alphas=True), -4.0))
-    assert _last_kernel() == "general"
+    assert _last_kernel() == "tc"          # d_hidden 32 + one ResnetFC block: the block runs as two more MMA rounds
 
 
 def test_cfg5_slice_one_million_rays():
@@ -315,3 +315,22 @@ def test_cfg5_slice_one_million_rays():
     got = {k: v.cpu() for k, v in got.items()}
     ref = pu.oracle_render(sub, sd, want_weights=True)
     print(pu.compare_render(sub, got, ref, label="cfg5 slice"))
+
+
+@pytest.mark.parametrize("name,kernel", [("cfg4_small", "tc"), ("dist_block1", "tc"), ("cfg2_small_bias4", "band"), ("cfg3_small_n2", "tc")])
+def test_fixture_kernel_dispatch(name, kernel):
+    """Which kernel family renders which reference fixture: the RealEstate10K field (d_hidden 32, one ResnetFC block, distance
+    code, K = 128) and the 64-wide block variant run on the tensor-core gather kernel (block = two more MMA rounds), single-frame
+    KITTI scenes on the band kernel, batched scenes on the gather kernel.  Fast tier of the block variants within its tolerance."""
+    g = load_golden(name)
+    wl = pu.workload_from_golden(g)
+    _, _, got = pu.cuda_render(wl, state_dict=g.sd, **ALL)
+    assert _last_kernel() == kernel
+    print(name, pu.compare_render(wl, got, g.out, label=name))
+    if kernel == "tc":
+        _, _, fast = pu.cuda_render(wl, state_dict=g.sd, precision=1, want_weights=True)
+        assert _last_kernel() == "tc"
+        same = (fast["invalid"] == g.out["invalid"]).flatten(2).all(-1)
+        rel = ((fast["depth"] - g.out["depth"]).abs() / g.out["depth"])[same]
+        assert rel.mean().item() <= 1e-3, rel.mean().item()
+    assert _lib.load().bts_debug_tc_timeouts() == 0
