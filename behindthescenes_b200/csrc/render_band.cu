@@ -11,7 +11,7 @@
 //      h[128 samples x Hd] = PE[128 x 48]·W_pe  +  A_w[128 x 16·steps] · Band[16·steps x Hd]
 //
 //   * Band: G is kept a second time as fp16 hi + lo operand blocks (bts_pack_g16: one 2·Hd·16-byte block per 8 pixels of
-//     a row, K-major core matrices; two copies whose blocks start at 0 and at 4 mod 8 so that any 29-pixel span fits 4
+//     a row, K-major core matrices; three copies with the pixels shifted by 0, 3 and 6 so that any 30-pixel span fits 4
 //     blocks).  One cp.async.bulk per band row (TMA engine, mbarrier complete_tx) brings the blocks the tile needs into
 //     shared memory, ready to be the B operand: no per-lane loads, no address arithmetic.
 //   * A_w: every sample scatters its 4 bilinear weights (fp16 hi + lo) into its row of a zeroed K-major operand tile
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
   const BtsRenderCfg& cfg = p.cfg;
   const int C = p.mlp.C, ld = C + p.mlp.P;
   const int K = cfg.n_coarse, Vc = p.scene.Vc, Cc = p.scene.Cc;
-  const int H = p.scene.H, W = p.scene.W, Wo = (W + 4 + 7) >> 3;   // blocks per row in either copy of G16
+  const int H = p.scene.H, W = p.scene.W, Wo = (W + 6 + 7) >> 3;   // blocks per row in every copy of G16
 
   // ---- one-time setup: weights -> B operands, tables, zeroed operand tiles, TMEM, mbarriers ----
   for (int i = tid; i < HD * 48; i += kThreads) {
@@ -357,7 +357,10 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
       const int xl = min(min(b0.x, b1.x), min(b2.x, b3.x)), xh = max(max(b0.y, b1.y), max(b2.y, b3.y));
       const int yl = min(min(b0.z, b1.z), min(b2.z, b3.z)), yh = max(max(b0.w, b1.w), max(b2.w, b3.w));
       Geom g;
-      g.xs = xl & 4;                       // the copy of G16 whose blocks start at 4 mod 8 when the span starts there
+      // three copies of G16 whose blocks start at 0, 5 and 2 mod 8 (pixels shifted by 0, 3, 6): the one that leaves the span
+      // at most 2 pixels into its first block, so any span <= 30 pixels fits kTmax = 4 blocks
+      const int r = xl & 7;
+      g.xs = r < 2 ? 0 : (r < 5 ? 6 : 3);
       g.ob = (xl + g.xs) >> 3; g.no = ((xh + g.xs) >> 3) - g.ob + 1; g.yb = yl;
       g.nsteps = xh >= xl ? ((yh - yl + 2) >> 1) * g.no : 0;       // row pairs x blocks
       return g;
@@ -368,7 +371,7 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
         const int rows_all = 2 * (g.nsteps / g.no);
         const int nrows = rows_all < H - g.yb ? rows_all : H - g.yb;
         tc::mbar_expect_tx(bar_tma, row_bytes * (uint32_t)nrows);
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.scene.G16) + (g.xs ? copy_bytes : 0) +
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.scene.G16) + (size_t)(g.xs / 3) * copy_bytes +
                                    ((size_t)g.yb * Wo + g.ob) * Lt::kBlk;
         for (int r = 0; r < nrows; ++r)
           tc::bulk_load(s_band + r * row_bytes, src + (size_t)r * Wo * Lt::kBlk, row_bytes, bar_tma);
@@ -702,16 +705,16 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
   if (tid < 32) tc::tmem_dealloc<Lt::kTmemCols>(*tmem_slot);
 }
 
-// G (n, H, W, HD) fp32 -> operand blocks, two copies (blocks starting at 0 and at 4 mod 8, the second shifted left by 4
-// pixels): thread = (copy, row, block, channel): 8 strided loads, two 16-byte stores.
+// G (n, H, W, HD) fp32 -> operand blocks, three copies (pixels shifted right by 0, 3 and 6: block o of copy s covers pixels
+// 8 o - 3 s .. 8 o - 3 s + 7): thread = (copy, row, block, channel): 8 strided loads, two 16-byte stores.
 template <int HD>
 __global__ void pack_g16_kernel(const float* __restrict__ G, int64_t rows, int W, int Wo, unsigned char* __restrict__ out,
                                 int32_t* __restrict__ flags) {
-  const int64_t per_copy = rows * Wo * HD, total = 2 * per_copy;
+  const int64_t per_copy = rows * Wo * HD, total = 3 * per_copy;
   bool bad = false;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int shift = i >= per_copy ? 4 : 0;
-    const int64_t ii = i - (shift ? per_copy : 0);
+    const int copy = (int)(i / per_copy), shift = 3 * copy;
+    const int64_t ii = i - copy * per_copy;
     const int c = (int)(ii % HD);
     const int64_t oi = ii / HD;                // row * Wo + block
     const int o = (int)(oi % Wo);
@@ -732,7 +735,7 @@ __global__ void pack_g16_kernel(const float* __restrict__ G, int64_t rows, int W
       hi[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
       lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&l);
     }
-    unsigned char* blk = out + (shift ? per_copy * 32 : 0) + oi * (32 * HD) + (c >> 3) * 128 + (c & 7) * 16;
+    unsigned char* blk = out + (copy * per_copy + oi * HD) * 32 + (c >> 3) * 128 + (c & 7) * 16;
     *reinterpret_cast<uint4*>(blk) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(blk + 16 * HD) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
@@ -780,14 +783,14 @@ cudaError_t launch_band(const KernelParams& p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-// two copies (block starts at 0 and at 4 mod 8), each (n*H rows) x ceil((W+4)/8) blocks of 32*Hd bytes
-int64_t g16_bytes(int n, int H, int W, int Hd) { return 2 * (int64_t)n * H * ((W + 4 + 7) / 8) * 32 * Hd; }
+// three copies (pixels shifted by 0, 3, 6), each (n*H rows) x ceil((W+6)/8) blocks of 32*Hd bytes
+int64_t g16_bytes(int n, int H, int W, int Hd) { return 3 * (int64_t)n * H * ((W + 6 + 7) / 8) * 32 * Hd; }
 
 cudaError_t launch_pack_g16(const float* G, int n, int H, int W, int Hd, void* out, int32_t* flags, cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(int32_t), stream);
   if (e != cudaSuccess) return e;
-  const int Wo = (W + 4 + 7) / 8;
-  const int64_t rows = (int64_t)n * H, total = 2 * rows * Wo * Hd;
+  const int Wo = (W + 6 + 7) / 8;
+  const int64_t rows = (int64_t)n * H, total = 3 * rows * Wo * Hd;
   const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   if (Hd == 64) band::pack_g16_kernel<64><<<grid, 256, 0, stream>>>(G, rows, W, Wo, static_cast<unsigned char*>(out), flags);
   else band::pack_g16_kernel<128><<<grid, 256, 0, stream>>>(G, rows, W, Wo, static_cast<unsigned char*>(out), flags);

@@ -13,8 +13,9 @@
  *   G      (n, H, W, Hd)      "folded feature map": G[p] = W_in[:, :C] * F[:, p] + b_in   (bts_fold_features)
  *   g_empty(Hd)               W_in[:, :C] * empty_feature + b_in                      (learn_empty)
  *   img4   (n, Vc, Hc, Wc, 4) colour views, channels-last padded to 4                (bts_pack_images)
- *   G16    (n*H, ceil(W/8), 2, Hd/8, 8, 8) fp16: G as tcgen05 operand blocks, one per octet of 8 pixels:
- *          [plane hi|lo][channel group][channel][pixel] (K-major core matrices, hi + lo = fp32-grade)  (bts_pack_g16)
+ *   G16    3 x (n*H, ceil((W+6)/8), 2, Hd/8, 8, 8) fp16: G as tcgen05 operand blocks of 8 pixels of a row,
+ *          [plane hi|lo][channel group][channel][pixel] (K-major core matrices, hi + lo = fp32-grade); three copies with the
+ *          pixels shifted by 0, 3 and 6 so that a 30-pixel span always fits 4 blocks               (bts_pack_g16)
  *   K_*    (n, V, 3, 3), w2c_* (n, V, 4, 4) row-major camera matrices as the reference caches them
  */
 #ifndef BTS_B200_H_

@@ -47,7 +47,7 @@ def test_struct_mirrors_match_header_layout():
     assert ctypes.sizeof(_lib.BtsRenderOut) == 10 * 8 + 8 + 8              # + scratch, scratch_ints
     assert ctypes.sizeof(_lib.BtsRayGen) == 2 * 8 + 4 * 4 + 2 * 4
     assert ctypes.sizeof(_lib.BtsRenderCfg) == 9 * 4 + 6 * 4 + 4 + 8 + 8 + 8 + 8  # 9 ints, 6 floats, pad, z_steps, step+band_mode, seed_dev, precision+pad
-    assert lib_g16_bytes() == 2 * 192 * 81 * 2048        # two copies, ceil((640 + 4) / 8) blocks per row
+    assert lib_g16_bytes() == 3 * 192 * 81 * 2048        # three copies, ceil((640 + 6) / 8) blocks per row
 
 
 def lib_g16_bytes():
