@@ -98,6 +98,21 @@ __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
 __device__ __forceinline__ void ffma2(uint64_t& acc, uint64_t a, uint64_t b) {
   asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
 }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
 __device__ __forceinline__ float2 unpack2(uint64_t v) {
   float2 r;
   asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
@@ -387,18 +402,29 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
       uint32_t ahi[24], alo[24];
 #pragma unroll
       for (int i = 18; i < 24; ++i) { ahi[i] = 0u; alo[i] = 0u; }
+      // one accurate sincos per coordinate, then exact double-angle steps per octave; the recurrences of u and v run as
+      // packed fp32 pairs (FADD2 / FMUL2: same IEEE operations, half the issue slots), the depth code's as scalars
+      float s0, c0, s1, c1, s2, c2;
+      sincos_moderate(__fmul_rn(pv[0], cfg.freq_factor), s0, c0);
+      sincos_moderate(__fmul_rn(pv[1], cfg.freq_factor), s1, c1);
+      sincos_moderate(__fmul_rn(pv[2], cfg.freq_factor), s2, c2);
+      uint64_t S = pack2(s0, s1), C = pack2(c0, c1);
 #pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        float s, c;
-        sincos_moderate(__fmul_rn(pv[d], cfg.freq_factor), s, c);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          if (kExact) split_h2(s, c, ahi[d * 6 + i], alo[d * 6 + i]);
-          else ahi[d * 6 + i] = pack_h2(s, c);
-          const float s2 = (s + s) * c;
-          c = (c - s) * (c + s);
-          s = s2;
+      for (int i = 0; i < 6; ++i) {
+        const float2 sv = unpack2(S), cv = unpack2(C);
+        if (kExact) {
+          split_h2(sv.x, cv.x, ahi[0 * 6 + i], alo[0 * 6 + i]);
+          split_h2(sv.y, cv.y, ahi[1 * 6 + i], alo[1 * 6 + i]);
+          split_h2(s2, c2, ahi[2 * 6 + i], alo[2 * 6 + i]);
+        } else {
+          ahi[0 * 6 + i] = pack_h2(sv.x, cv.x); ahi[1 * 6 + i] = pack_h2(sv.y, cv.y); ahi[2 * 6 + i] = pack_h2(s2, c2);
         }
+        const uint64_t S2 = mul2(add2(S, S), C);
+        C = mul2(sub2(C, S), add2(C, S));
+        S = S2;
+        const float t2 = (s2 + s2) * c2;
+        c2 = (c2 - s2) * (c2 + s2);
+        s2 = t2;
       }
       // raw coordinates (|p| <= 8): exact three-term fp16 split h + l + l2 in columns 36..44 of the hi operand
       __half r[9];
