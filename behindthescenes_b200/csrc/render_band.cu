@@ -272,6 +272,11 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
   const float b_out = __ldg(p.mlp.b_out);
   const bool use_empty = cfg.learn_empty && p.scene.g_empty != nullptr;
   const uint32_t idesc16 = tc::instr_desc(tc::kFmtF16, 128, HD);
+  // Side jobs of a tile group (MMA issue, band copies) go to different warps in different groups: warp w of every CTA runs on
+  // scheduler w % 4, so fixed roles would pile all four resident groups' issue work onto scheduler 0.  CTAs of the second half
+  // of the grid are the ones that share an SM with the first half (2 CTAs per SM, grid = 2 x SMs).
+  const int role = group + (blockIdx.x >= (gridDim.x >> 1) ? 2 : 0);
+  const int mma_warp = role & 3, tma_warp = (role + 2) & 3;
   const bool g16_bad = p.scene.g16_flags != nullptr && __ldg(p.scene.g16_flags) != 0;
   const uint32_t sW = tc::smem_u32(smem), sBand = tc::smem_u32(s_band), sAw = tc::smem_u32(s_aw);
   // operand descriptor of the first positional-code weight chunk pair; the others differ only in the start address
@@ -381,15 +386,19 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
       return g;
     };
     auto issue_band = [&](const Geom& g) {   // one bulk copy per band row: `no` consecutive blocks of G16
-      if (gt == 32 && g.nsteps > 0) {      // warp 1 (warp 0 issues the MMAs)
-        const uint32_t row_bytes = (uint32_t)g.no * Lt::kBlk;
-        const int rows_all = 2 * (g.nsteps / g.no);
-        const int nrows = rows_all < H - g.yb ? rows_all : H - g.yb;
-        tc::mbar_expect_tx(bar_tma, row_bytes * (uint32_t)nrows);
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.scene.G16) + (size_t)(g.xs / 3) * copy_bytes +
-                                   ((size_t)g.yb * Wo + g.ob) * Lt::kBlk;
-        for (int r = 0; r < nrows; ++r)
-          tc::bulk_load(s_band + r * row_bytes, src + (size_t)r * Wo * Lt::kBlk, row_bytes, bar_tma);
+      if (__shfl_sync(kFull, warp, 0) == tma_warp) {       // whole warp (uniform operands), one elected lane issues
+        const int nsteps_u = __shfl_sync(kFull, g.nsteps, 0), no_u = __shfl_sync(kFull, g.no, 0);
+        const int yb_u = __shfl_sync(kFull, g.yb, 0), ob_u = __shfl_sync(kFull, g.ob, 0), xs_u = __shfl_sync(kFull, g.xs, 0);
+        if (nsteps_u > 0 && tc::elect_one()) {
+          const uint32_t row_bytes = (uint32_t)no_u * Lt::kBlk;
+          const int rows_all = 2 * (nsteps_u / no_u);
+          const int nrows = rows_all < H - yb_u ? rows_all : H - yb_u;
+          tc::mbar_expect_tx(bar_tma, row_bytes * (uint32_t)nrows);
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(p.scene.G16) + (size_t)(xs_u / 3) * copy_bytes +
+                                     ((size_t)yb_u * Wo + ob_u) * Lt::kBlk;
+          for (int r = 0; r < nrows; ++r)
+            tc::bulk_load(s_band + r * row_bytes, src + (size_t)r * Wo * Lt::kBlk, row_bytes, bar_tma);
+        }
       }
     };
     // P1a: positional code of (u, v, code) -> A operand in TMEM
@@ -504,35 +513,40 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
       const uint32_t sample_id = (uint32_t)ray * (uint32_t)K + (uint32_t)k;   // < 2^31 elements per output (launcher)
       group_sync(group);                   // operands of this tile complete; the previous tile is fully consumed
       // ---------------- MMA issue (one thread of the group) ----------------
-      if (gt == 0) {
+      if (__shfl_sync(kFull, warp, 0) == mma_warp) {   // whole warp (uniform operands), one elected lane issues
+        const int nsteps_u = __shfl_sync(kFull, geom.nsteps, 0), no_u = __shfl_sync(kFull, geom.no, 0);
+        const bool leader = tc::elect_one();
         tc::tc_fence_after_sync();
+        if (leader) {
 #pragma unroll
-        for (int ks = 0; ks < 3; ++ks) {
-          tc::mma_f16_ts(tD, tAhi + ks * 8, d_w + ks * kStepW, idesc16, ks > 0);
-          if (kExact) {
-            tc::mma_f16_ts(tD, tAlo + ks * 8, d_w + ks * kStepW, idesc16, 1);
-            tc::mma_f16_ts(tD, tAhi + ks * 8, d_w + ks * kStepW + kLoW, idesc16, 1);
-          }
-        }
-        if (geom.nsteps > 0) {
-          tc::mbar_wait_or_trap(bar_tma, tma_phase, &g_band_barrier_timeouts);   // the band has landed
-          const uint32_t row_bytes = (uint32_t)geom.no * Lt::kBlk;
-          uint32_t a_base = sAw, b_base = sBand;
-          int oct = 0;
-          for (int ts = 0; ts < geom.nsteps; ++ts) {
-            const uint64_t a_hi = tc::smem_desc_kmajor_noswizzle(a_base, kChunkA, 128);
-            const uint64_t b_hi = tc::smem_desc_kmajor_noswizzle(b_base, row_bytes, 128);
-            tc::mma_f16_ss(tD, a_hi, b_hi, idesc16, 1);
+          for (int ks = 0; ks < 3; ++ks) {
+            tc::mma_f16_ts(tD, tAhi + ks * 8, d_w + ks * kStepW, idesc16, ks > 0);
             if (kExact) {
-              tc::mma_f16_ss(tD, a_hi + Lt::kPlaneA / 16, b_hi, idesc16, 1);
-              tc::mma_f16_ss(tD, a_hi, b_hi + Lt::kPlaneB / 16, idesc16, 1);
+              tc::mma_f16_ts(tD, tAlo + ks * 8, d_w + ks * kStepW, idesc16, 1);
+              tc::mma_f16_ts(tD, tAhi + ks * 8, d_w + ks * kStepW + kLoW, idesc16, 1);
             }
-            a_base += 2 * kChunkA;
-            b_base += Lt::kBlk;
-            if (++oct == geom.no) { oct = 0; b_base += row_bytes; }   // next row pair
           }
         }
-        tc::mma_commit(bar_mma);
+        if (nsteps_u > 0) {
+          tc::mbar_wait_or_trap(bar_tma, tma_phase, &g_band_barrier_timeouts);   // the band has landed
+          if (leader) {
+            const uint32_t row_bytes = (uint32_t)no_u * Lt::kBlk;
+            uint64_t a_hi = tc::smem_desc_kmajor_noswizzle(sAw, kChunkA, 128);
+            uint64_t b_hi = tc::smem_desc_kmajor_noswizzle(sBand, row_bytes, 128);
+            int oct = 0;
+            for (int ts = 0; ts < nsteps_u; ++ts) {
+              tc::mma_f16_ss(tD, a_hi, b_hi, idesc16, 1);
+              if (kExact) {
+                tc::mma_f16_ss(tD, a_hi + Lt::kPlaneA / 16, b_hi, idesc16, 1);
+                tc::mma_f16_ss(tD, a_hi, b_hi + Lt::kPlaneB / 16, idesc16, 1);
+              }
+              a_hi += 2 * kChunkA / 16;
+              b_hi += Lt::kBlk / 16;
+              if (++oct == no_u) { oct = 0; b_hi += row_bytes / 16; }   // next row pair
+            }
+          }
+        }
+        if (leader) tc::mma_commit(bar_mma);
       }
       if (geom.nsteps > 0) tma_phase ^= 1u;
       __syncwarp();

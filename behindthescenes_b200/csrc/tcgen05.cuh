@@ -115,6 +115,17 @@ __host__ __device__ constexpr uint32_t instr_desc(uint32_t fmt_ab, uint32_t M, u
          | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// One lane of a converged warp (warp-uniform control flow lets the compiler keep MMA operands in uniform registers).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- MMA issue (one thread) ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
