@@ -89,6 +89,9 @@ __global__ void __launch_bounds__(kThreads, 2) render_bwd_tc_kernel(const BwdPar
   const KernelParams& p = bp.k;
   const BtsRenderCfg& cfg = p.cfg;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // the MMA-issuing warp differs between the CTAs that share an SM (warp w runs on scheduler w % 4)
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const int mma_warp = (int)(blockIdx.x / tc::num_sms()) & 3;
   const int K = cfg.n_coarse, Kpad = (K + 31) & ~31;
   const int C = p.mlp.C, P = p.mlp.P, ld = C + P;
   const int Vc = p.scene.Vc, Cc = p.scene.Cc;
@@ -357,7 +360,7 @@ __global__ void __launch_bounds__(kThreads, 2) render_bwd_tc_kernel(const BwdPar
       }
       tc::tc_fence_before_sync();
       __syncthreads();
-      if (tid == 0) {
+      if (warp_u == mma_warp && tc::elect_one()) {   // converged warp, one elected lane: operands stay in uniform registers
         tc::tc_fence_after_sync();
         const uint32_t sW = tc::smem_u32(smem);
 #pragma unroll
@@ -465,7 +468,7 @@ __global__ void __launch_bounds__(kThreads, 2) render_bwd_tc_kernel(const BwdPar
       tc::fence_proxy_async_smem();        // operand tiles (P1: lbar*code, P3: mask) -> async proxy
       tc::tc_fence_before_sync();
       __syncthreads();
-      if (tid == 0) {
+      if (warp_u == mma_warp && tc::elect_one()) {   // converged warp, one elected lane: operands stay in uniform registers
         tc::tc_fence_after_sync();
         const uint32_t sW = tc::smem_u32(smem);
 #pragma unroll

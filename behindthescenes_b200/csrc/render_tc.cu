@@ -94,6 +94,9 @@ __global__ void __launch_bounds__(kThreads, L<HD, NB>::kCtasPerSm) render_tc_ker
   constexpr int kGiStride = Lt::kGiStride, kLPS = Lt::kLanesPerSample, kSPI = Lt::kSamplesPerIter;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // the MMA-issuing warp differs between the CTAs that share an SM (warp w runs on scheduler w % 4)
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const int mma_warp = (int)(blockIdx.x / tc::num_sms()) & 3;
   // work-list mode: render only the 8-ray groups the band kernel (render_band.cu) handed over; one group = 2 passes
   const int work_groups = (!kPoints && p.work_mode) ? *reinterpret_cast<const volatile int32_t*>(p.work) : 0;
   if (!kPoints && p.work_mode && (int)blockIdx.x >= 2 * work_groups) return;
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, L<HD, NB>::kCtasPerSm) render_tc_ker
       __syncthreads();                     // all 128 rows of the A tile are in TMEM; D of the previous tile is consumed
 
       // ---------------- MMA issue (one thread) ----------------
-      if (tid == 0) {
+      if (warp_u == mma_warp && tc::elect_one()) {   // converged warp, one elected lane: operands stay in uniform registers
         tc::tc_fence_after_sync();
         const uint32_t sW = tc::smem_u32(smem);
 #pragma unroll
@@ -502,7 +505,7 @@ __global__ void __launch_bounds__(kThreads, L<HD, NB>::kCtasPerSm) render_tc_ker
           auto block_mma = [&](int m) {
             tc::tc_fence_before_sync();
             __syncthreads();
-            if (tid == 0) {
+            if (warp_u == mma_warp && tc::elect_one()) {   // converged warp, one elected lane: operands stay in uniform registers
               tc::tc_fence_after_sync();
               const uint32_t sB = tc::smem_u32(smem) + Lt::kOffBlk + 2 * m * Lt::kBlkPlane;
 #pragma unroll

@@ -115,6 +115,12 @@ __host__ __device__ constexpr uint32_t instr_desc(uint32_t fmt_ab, uint32_t M, u
          | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// SMs of the device (%nsmid): CTA b of a persistent grid of k x SMs CTAs shares its SM with the CTAs b + j * SMs
+__device__ __forceinline__ uint32_t num_sms() {
+  uint32_t n;
+  asm("mov.u32 %0, %%nsmid;" : "=r"(n));
+  return n;
+}
 // One lane of a converged warp (warp-uniform control flow lets the compiler keep MMA operands in uniform registers).
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
