@@ -335,8 +335,8 @@ class BTSNet(nn.Module):
                     self.empty_feature if self.learn_empty else None]
             blk = list(m.blocks[0].fc_0.parameters()) + list(m.blocks[0].fc_1.parameters()) if m.n_blocks == 1 else []
             if any(t is not None and t.requires_grad for t in diff + blk):
-                if not (m.n_blocks == 0 and m.d_hidden <= 64) and not (m.n_blocks == 1 and m.d_hidden == 32):
-                    raise NotImplementedError("backward of the B200 render path implements n_blocks=0 (d_hidden<=64) and "
+                if not (m.n_blocks == 0 and m.d_hidden <= 128) and not (m.n_blocks == 1 and m.d_hidden == 32):
+                    raise NotImplementedError("backward of the B200 render path implements n_blocks=0 (d_hidden<=128) and "
                                               "n_blocks=1 with d_hidden=32 (the shipped KITTI / RE10K training configs)")
                 keys = ["rgb", "depth"] + [k for k, w in (("invalid", diet.get("want_invalid", True)),
                                                           ("invalid_mass", diet.get("want_invalid_mass", False)),

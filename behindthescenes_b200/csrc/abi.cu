@@ -181,8 +181,8 @@ int bts_render_bwd(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg*
   if (!rays || !upstream || !grads) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_render_bwd: rays/upstream/grads is null");
   if (n != scene->n) return fail(BTS_ERR_INVALID_ARGUMENT, "rays batch %lld != scene.n %d", (long long)n, scene->n);
   if (cfg->n_coarse < 1 || !cfg->z_steps) return fail(BTS_ERR_INVALID_ARGUMENT, "n_coarse < 1 or z_steps null");
-  if (!(mlp->n_blocks == 0 && mlp->Hd <= 64) && !(mlp->n_blocks == 1 && mlp->Hd == 32))
-    return fail(BTS_ERR_UNSUPPORTED, "backward implements n_blocks=0 with d_hidden<=64, or n_blocks=1 with d_hidden=32 (got %d, %d)",
+  if (!(mlp->n_blocks == 0 && mlp->Hd <= 128) && !(mlp->n_blocks == 1 && mlp->Hd == 32))
+    return fail(BTS_ERR_UNSUPPORTED, "backward implements n_blocks=0 with d_hidden<=128, or n_blocks=1 with d_hidden=32 (got %d, %d)",
                 mlp->n_blocks, mlp->Hd);
   if (mlp->n_blocks == 1 && !(grads->d_fc0_w && grads->d_fc0_b && grads->d_fc1_w && grads->d_fc1_b))
     return fail(BTS_ERR_INVALID_ARGUMENT, "block gradients (d_fc0_*, d_fc1_*) are null");

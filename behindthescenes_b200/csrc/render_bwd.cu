@@ -499,6 +499,8 @@ cudaError_t launch_bwd(const BwdParams& bp, cudaStream_t stream, bool* used_tc) 
   switch (bp.k.mlp.Hd / 32) {
     case 1: return launch_bwd_t<1, false>(bp, stream);
     case 2: return launch_bwd_t<2, false>(bp, stream);
+    case 3: return launch_bwd_t<3, false>(bp, stream);
+    case 4: return launch_bwd_t<4, false>(bp, stream);
   }
   return cudaErrorInvalidValue;
 }

@@ -252,21 +252,39 @@ def run_ours(args):
     metric_acc = torch.zeros(2, device=dev, dtype=torch.float64)
     side = torch.cuda.Stream(dev)
 
+    def frame_step():
+        net.invalidate_scene()                                         # a new frame: fold + pack run again
+        net._scene_struct()
+        return wrapped(rays_dev, **wants)["coarse"]
+
+    graph = {"replay": None, "out": None, "read": None}
+
     def one_step(timed, ev=None):
         flush.fill_(1)                                                 # evict L2 (126 MB) -- outside the event pair
-        net.invalidate_scene()                                         # a new frame: fold + pack run again
-        if ev:
-            ev[0].record()
-        net._scene_struct()
-        if ev:
-            ev[1].record()
-        out = wrapped(rays_dev, **wants)["coarse"]
+        if graph["replay"] is not None:                                # the whole step (6 launches) as ONE graph launch
+            if graph["read"] is not None:                              # the replay overwrites the outputs the side stream
+                torch.cuda.current_stream(dev).wait_event(graph["read"])   # summed (done long ago: an ordering, not a wait)
+            if ev:
+                ev[0].record()
+            graph["replay"]()
+            out = graph["out"]
+        else:
+            net.invalidate_scene()
+            if ev:
+                ev[0].record()
+            net._scene_struct()
+            if ev:
+                ev[1].record()
+            out = wrapped(rays_dev, **wants)["coarse"]
         done = ev[2] if ev else torch.cuda.Event()
         done.record()                                                  # end of the step on the compute stream
         side.wait_event(done)
         with torch.cuda.stream(side):
             metric_acc[0] += out["depth"].sum(dtype=torch.float64)
             metric_acc[1] += float(n_rays)
+            if graph["replay"] is not None:
+                graph["read"] = torch.cuda.Event()
+                graph["read"].record(side)
         out["depth"].record_stream(side)
         return out
 
@@ -317,9 +335,38 @@ def run_ours(args):
     kern_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
 
     with torch.no_grad():
+        # eager steps first: they give the fold+pack / render split of a step (events between the launches) and bring the
+        # caching allocator to its steady state
+        evw = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(max(args.warmup, 3))]
+        for e in evw:
+            out = one_step(False, e)
+        finish_metric()
+        sync_all()
+        med = lambda v: sorted(v)[len(v) // 2]        # the first eager steps after the kernel loop still grow the allocator
+        prep_ms = med([e[0].elapsed_time(e[1]) for e in evw])
+        render_ms = med([e[1].elapsed_time(e[2]) for e in evw])
+        eager_step_ms = med([e[0].elapsed_time(e[2]) for e in evw])
+        if not args.no_graph:
+            # the timed step is one CUDA-graph launch (fold, fold_empty, pack_g16, pack_images, render_band, work-list
+            # pass): no host-side gaps between the six launches, whatever the box's CPU load (8 ranks share the host)
+            try:
+                st = torch.cuda.Stream(dev)
+                st.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(st):
+                    frame_step()
+                torch.cuda.current_stream(dev).wait_stream(st)
+                torch.cuda.synchronize(dev)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    graph["out"] = frame_step()
+                graph["replay"] = g.replay
+            except Exception as exc:   # capture is an optimisation of the loop, never a requirement
+                print(f"bench: CUDA-graph capture failed ({exc}); timing eager steps", file=sys.stderr)
+                torch.cuda.synchronize(dev)
+                graph["replay"] = None
         for _ in range(max(args.warmup, 3)):
-            out = one_step(False)              # keep the results alive exactly like the timed loop does: the caching
-        finish_metric()                        # allocator must reach its steady state (two output sets) before timing
+            out = one_step(False)              # warm-up of the timed form of the step
+        finish_metric()
         sync_all()
         metric_acc.zero_()
         evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
@@ -329,14 +376,13 @@ def run_ours(args):
         metric, fin = finish_metric()
         sync_all()
         wall = time.perf_counter() - t_wall0
-    prep_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
-    render_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
     # what the metric adds to the job: the part of the side-stream work that outlasts the last step
     metric_tail_ms = max(0.0, evs[-1][2].elapsed_time(fin))
-    per_step_render = sorted(e[1].elapsed_time(e[2]) for e in evs)
+    per_step = sorted(e[0].elapsed_time(e[2]) for e in evs)
     mem = torch.cuda.memory_stats(dev)
-    diag = {"render_ms_min": per_step_render[0], "render_ms_median": per_step_render[len(per_step_render) // 2],
-            "render_ms_max": per_step_render[-1], "first_steps_ms": [round(e[1].elapsed_time(e[2]), 3) for e in evs[:6]],
+    diag = {"step_ms_min": per_step[0], "step_ms_median": per_step[len(per_step) // 2], "step_ms_max": per_step[-1],
+            "first_steps_ms": [round(e[0].elapsed_time(e[2]), 3) for e in evs[:6]], "ms_per_step_eager": eager_step_ms,
+            "cuda_graph": graph["replay"] is not None,
             "cuda_mallocs": mem.get("num_device_alloc", -1), "alloc_retries": mem.get("num_alloc_retries", -1)}
     step_ms = (sum(e[0].elapsed_time(e[2]) for e in evs) + metric_tail_ms) / args.steps
     handed = int(net._band_work[0].item()) if getattr(net, "_band_work", None) is not None else None
@@ -383,14 +429,48 @@ def run_ours(args):
     # The same steps as a 3-stage stream pipeline (how a serving loop runs them): H2D of frame i+1 and D2H of frame i-1
     # overlap the render of frame i on separate streams; every step still moves its own inputs and its own result.
     # No L2 flush here: the per-step inputs rotate over 5 feature maps (5 x 31.5 MB > L2) and arrive by DMA.
-    feats_rot = [torch.randn_like(net.grid_f_features[0]) for _ in range(5)]
+    slots = 5
+    feats_rot = [torch.randn_like(net.grid_f_features[0]) for _ in range(slots)]
     s_in, s_c, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    slots = 3
     img_d = [torch.empty_like(img_dev) for _ in range(slots)]
     pos_d = [torch.empty_like(poses_dev) for _ in range(slots)]
     Ks_d = [torch.empty_like(Ks_dev) for _ in range(slots)]
     dep_h = [torch.empty_like(depth_host).pin_memory() for _ in range(slots)]
     rgb_h = [torch.empty_like(rgb_host).pin_memory() for _ in range(slots)]
+
+    def compute_stage(j):
+        """the device part of a step through the public API: colour cache of encode(), fold + pack, render_views"""
+        net.grid_f_features = [feats_rot[j]]
+        net.grid_c_imgs = net._take_views(img_d[j] * 0.5 + 0.5, wl.ids_render)
+        net.invalidate_scene()
+        return wrapped.render_views(pos_d[j], Ks_d[j], H_img, W_img, wl.model_conf["z_near"], wl.model_conf["z_far"],
+                                    want_depth_z=True, **wants)["coarse"]
+
+    # One CUDA graph per slot (its buffers are fixed): the compute stage is ONE launch per step, so the pipeline's period
+    # is the GPU's and not the host's enqueue rate (~14 launches + Python per 1.1 ms step; 8 ranks share the host)
+    stage_graphs = None
+    if not args.no_graph:
+        try:
+            with torch.no_grad():
+                for b in img_d + pos_d + Ks_d:
+                    b.zero_()
+                torch.cuda.synchronize(dev)
+                gs = []
+                for j in range(slots):
+                    img_d[j].copy_(img_host); pos_d[j].copy_(poses_host); Ks_d[j].copy_(Ks_host)
+                    s_c.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(s_c):
+                        compute_stage(j)
+                    torch.cuda.synchronize(dev)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=s_c):
+                        o_j = compute_stage(j)
+                    gs.append((g, o_j))
+                stage_graphs = gs
+        except Exception as exc:
+            print(f"bench: e2e CUDA-graph capture failed ({exc}); eager compute stage", file=sys.stderr)
+            torch.cuda.synchronize(dev)
+            stage_graphs = None
     keep, ev_in, ev_c, ev_out = {}, {}, {}, {}
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_pipe = args.steps + 6
@@ -416,11 +496,13 @@ def run_ours(args):
                     t0.record(s_c)
                 if i == 3 + args.steps:
                     t1.record(s_c)
-                net.grid_f_features = [feats_rot[i % len(feats_rot)]]
-                net.grid_c_imgs = net._take_views(img_d[j] * 0.5 + 0.5, wl.ids_render)
-                net.invalidate_scene()
-                o = wrapped.render_views(pos_d[j], Ks_d[j], H_img, W_img, wl.model_conf["z_near"], wl.model_conf["z_far"],
-                                         want_depth_z=True, **wants)["coarse"]
+                if stage_graphs is not None:
+                    if i - slots in ev_out:
+                        s_c.wait_event(ev_out[i - slots])            # slot j's outputs have left for the host
+                    stage_graphs[j][0].replay()
+                    o = stage_graphs[j][1]
+                else:
+                    o = compute_stage(j)
                 ev_c[i] = torch.cuda.Event(); ev_c[i].record(s_c)
             keep[i] = o                                              # outputs stay alive until their D2H has been issued+done
             with torch.cuda.stream(s_out):
@@ -434,6 +516,7 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         sync_all()
     e2e_ms = t0.elapsed_time(t1) / args.steps
+    e2e_graph = stage_graphs is not None
     clocks = sampler.stop() if sampler else None                     # covers warm-up, timed loop, kernel loop, e2e loops
     gc.enable()
     h2d_bytes = int((img_host.numel() + poses_host.numel() + Ks_host.numel()) * 4)
@@ -480,12 +563,12 @@ def run_ours(args):
                 "config": {"workload": "cfg2 KITTI-360 eval_depth: 192x640 stereo frame, 245760 rays/GPU, K=64, outputs rgb+depth+invalid+weights+alphas",
                            "rays_per_gpu": n_rays, "samples_per_ray": K_SAMPLES, "parallelism": f"ray-shard x{world}",
                            "l2": "256 MiB flush before every timed step", "precision_tier": "exact-fp32" if args.precision == 0 else "fast",
-                           "kernel": kernel_name, "ms_fold_pack": prep_ms, "ms_render": render_ms,
+                           "kernel": kernel_name, "ms_fold_pack": prep_ms, "ms_render": render_ms, "step": "one CUDA-graph launch (6 kernels)" if diag["cuda_graph"] else "eager launches",
                            "ms_metric_tail": metric_tail_ms, "metric": "depth sum + ray count accumulated on a side stream, one NCCL all-reduce at the end",
                            "band_groups_handed_to_gather_kernel": handed, "diag": diag},
                 "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": int(depth_host.numel() * 4 + rgb_host.numel() * 4), "ms_per_step": e2e_ms,
-                        "how": "3-stream pipeline (H2D | fold+pack+render | D2H), every step copies its own inputs and result; steady-state period between compute starts of step 3 and step 3+steps",
+                        "how": "3-stream pipeline (H2D | fold+pack+render | D2H), every step copies its own inputs and result; compute stage = one CUDA-graph launch per step" + ("" if e2e_graph else " (capture failed: eager)") + "; steady-state period between compute starts of step 3 and step 3+steps",
                         "ms_per_step_unpipelined": e2e_seq_ms},
                 # ours, per step: fold, fold_empty, pack_g16, pack_images, render_band, render_tc (work-list pass)
                 "gpu_launches": args.steps * 6,
@@ -566,6 +649,7 @@ def main():
     ap.add_argument("--precision", type=int, default=0, help="0 exact-fp32 tier, 1 fast tier")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the eager-PyTorch-on-GPU reference leg")
+    ap.add_argument("--no-graph", action="store_true", help="time eager steps instead of one CUDA-graph launch per step")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (strong scaling, cfg3/4/5)")
     args = ap.parse_args()
     if args.impl == "reference":

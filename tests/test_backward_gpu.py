@@ -40,6 +40,21 @@ def cuda_gradients(wl, sd, precision=0, use_u=True, loss_fn=gu.probe_loss):
 GRAD_FIXTURES = [n for n in golden_names() if load_golden(n).grad]
 
 
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d_hidden", [96, 128])
+def test_backward_wide_field_vs_oracle_autograd(d_hidden):
+    """d_hidden 96 / 128 without blocks (the stress configuration's field width): the CUDA-core backward, 3 / 4 hidden units
+    per lane, against torch autograd through the oracle."""
+    wl = syn.cfg2_kitti360_eval(H=24, W=64, K=64, stereo=True, learn_empty=True, lin_out_bias=-4.0, seed=87, ray_subsample=500)
+    wl.model_conf["mlp_coarse"]["d_hidden"] = d_hidden
+    cpu_net, _ = syn.build_model(wl, "cpu")
+    sd = {k: v.clone() for k, v in cpu_net.state_dict().items() if not k.startswith("encoder.")}
+    got, _ = cuda_gradients(wl, sd)
+    ref = gu.oracle_gradients(wl, sd)
+    tol = gu.grad_tolerances(ref, gu.oracle_gradients64(wl, sd), GRAD_REL_TOL)
+    print(d_hidden, gu.assert_grads_close(got, ref, tol, f"d_hidden={d_hidden}"), "bounds", tol)
+
 @pytest.mark.parametrize("name", GRAD_FIXTURES)
 def test_backward_matches_reference_gradient_fixture(name):
     g = load_golden(name)
