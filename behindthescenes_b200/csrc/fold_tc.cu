@@ -25,8 +25,7 @@ __device__ int g_fold_barrier_timeouts = 0;
 
 namespace foldtc {
 
-constexpr int kThreads = 128;
-constexpr int kTile = 128;   // pixels per tile
+constexpr int kTile = 128;   // pixels per tile (one tile group = 128 threads)
 
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(smem_dst)),
@@ -42,30 +41,41 @@ struct L {
   static constexpr int kRaw = C * kTile * 4;                  // one raw tile: [C][128] floats
   static constexpr int kA = (C / 4) * kTile * 16;             // one operand tile: [C/4 chunks][128 rows][16 B]
   static constexpr int kW = (C / 4) * HD * 16;                // weights: [C/4 chunks][HD rows][16 B]
-  static constexpr int kOffRaw = 0;                           // x2
-  static constexpr int kOffAhi = 2 * kRaw;
-  static constexpr int kOffAlo = kOffAhi + kA;
-  static constexpr int kOffWhi = kOffAlo + kA;
+  static constexpr int kOffWhi = 0;
   static constexpr int kOffWlo = kOffWhi + kW;
   static constexpr int kOffBias = kOffWlo + kW;               // HD floats
-  static constexpr int kOffBar = kOffBias + HD * 4;           // full[2], mma : 3 mbarriers + tmem slot
-  static constexpr int kSmemBytes = kOffBar + 64;
-  static constexpr uint32_t kTmemCols = HD <= 32 ? 32 : (HD <= 64 ? 64 : 128);
+  static constexpr int kOffBar = kOffBias + HD * 4;           // per group: full, mma (2 mbarriers); then the tmem slot
+  static constexpr int kOffGroup = ((kOffBar + 64 + 127) / 128) * 128;
+  static constexpr int kGroupBytes = kRaw + 2 * kA;           // raw tile, operand hi, operand lo
+  // two independent tile pipelines per CTA when they fit: one group's transpose overlaps the other's MMA + epilogue
+  static constexpr int kGroups = (kOffGroup + 2 * kGroupBytes <= 227 * 1024) ? 2 : 1;
+  static constexpr int kThreads = kGroups * 128;
+  static constexpr int kSmemBytes = kOffGroup + kGroups * kGroupBytes;
+  // epilogue staging: the finished operand tiles hold the 128 output rows (padded: conflict-free 16-byte stores), each
+  // thread then hands its row to the copy engine (one 4*HD-byte bulk store: full lines instead of 16-byte partial writes)
+  static constexpr int kStageRow = HD * 4 + 16;
+  static constexpr bool kStage = 2 * kA >= kTile * kStageRow;
+  static constexpr uint32_t kGroupCols = HD <= 32 ? 32 : (HD <= 64 ? 64 : 128);
+  static constexpr uint32_t kTmemCols = kGroupCols * kGroups;
   static_assert(kSmemBytes <= 227 * 1024, "fold tile does not fit shared memory");
 };
 
 template <int HD, int C>
-__global__ void __launch_bounds__(kThreads, 1) fold_tc_kernel(const float* __restrict__ feat, int64_t HW, int n_batches,
-                                                               const float* __restrict__ w_in, int ld,
-                                                               const float* __restrict__ b_in, float* __restrict__ G,
-                                                               const __grid_constant__ CUtensorMap feat_map, int use_map) {
+__global__ void __launch_bounds__(L<HD, C>::kThreads, 1) fold_tc_kernel(const float* __restrict__ feat, int64_t HW, int n_batches,
+                                                                        const float* __restrict__ w_in, int ld,
+                                                                        const float* __restrict__ b_in, float* __restrict__ G,
+                                                                        const __grid_constant__ CUtensorMap feat_map, int use_map) {
   using Lt = L<HD, C>;
+  constexpr int kThreads = Lt::kThreads;
   extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, warp = tid >> 5;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Lt::kOffBar);        // [2]
-  uint64_t* mma_bar = full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 3);
+  const int tid = threadIdx.x, group = tid >> 7, gt = tid & 127, warp = gt >> 5;   // tile group, thread / warp inside it
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Lt::kOffBar) + 2 * group;
+  uint64_t* mma_bar = full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Lt::kOffBar + 32);
   float* s_bias = reinterpret_cast<float*>(smem + Lt::kOffBias);
+  unsigned char* g_raw = smem + Lt::kOffGroup + group * Lt::kGroupBytes;
+  unsigned char* g_ahi = g_raw + Lt::kRaw;
+  unsigned char* g_alo = g_ahi + Lt::kA;
 
   // ---- weights: tf32 hi/lo, K-major no-swizzle [chunk][n][4 floats]; bias ----
   for (int i = tid; i < HD * C; i += kThreads) {
@@ -77,10 +87,9 @@ __global__ void __launch_bounds__(kThreads, 1) fold_tc_kernel(const float* __res
     *reinterpret_cast<float*>(smem + Lt::kOffWlo + off) = w - hi;
   }
   for (int i = tid; i < HD; i += kThreads) s_bias[i] = __ldg(b_in + i);
-  if (warp == 0) tc::tmem_alloc<Lt::kTmemCols>(tmem_slot);
-  if (tid == 0) {
-    tc::mbar_init(&full[0], 1);
-    tc::mbar_init(&full[1], 1);
+  if (tid < 32) tc::tmem_alloc<Lt::kTmemCols>(tmem_slot);
+  if (gt == 0) {
+    tc::mbar_init(full, 1);
     tc::mbar_init(mma_bar, 1);
     tc::fence_mbar_init();
   }
@@ -88,65 +97,70 @@ __global__ void __launch_bounds__(kThreads, 1) fold_tc_kernel(const float* __res
   tc::tc_fence_before_sync();
   __syncthreads();
   tc::tc_fence_after_sync();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = *tmem_slot + group * Lt::kGroupCols;
   const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
   const uint32_t idesc = tc::instr_desc(tc::kFmtTF32, 128, HD);
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); };
 
   const int64_t tiles_per_b = (HW + kTile - 1) / kTile;
   const int64_t n_tiles = tiles_per_b * n_batches;
-  auto issue_load = [&](int64_t tile, int buf) {          // one elected thread: one tensor-map box (or C row copies)
+  auto issue_load = [&](int64_t tile) {                   // one elected thread: one tensor-map box (or C row copies)
     const int64_t b = tile / tiles_per_b, p0 = (tile % tiles_per_b) * kTile;
     const int valid = (int)((HW - p0) < kTile ? (HW - p0) : kTile);
-    unsigned char* dst = smem + Lt::kOffRaw + buf * Lt::kRaw;
     if (use_map) {
-      mbar_expect_tx(&full[buf], (uint32_t)Lt::kRaw);
-      tmap::load_tile_3d(dst, &feat_map, (int)p0, 0, (int)b, &full[buf]);
+      mbar_expect_tx(full, (uint32_t)Lt::kRaw);
+      tmap::load_tile_3d(g_raw, &feat_map, (int)p0, 0, (int)b, full);
       return;
     }
     const uint32_t row_bytes = (uint32_t)valid * 4u;
-    mbar_expect_tx(&full[buf], row_bytes * C);
+    mbar_expect_tx(full, row_bytes * C);
     const float* src = feat + ((size_t)b * C) * HW + p0;
-    for (int c = 0; c < C; ++c) bulk_load(dst + c * kTile * 4, src + (size_t)c * HW, row_bytes, &full[buf]);
+    for (int c = 0; c < C; ++c) bulk_load(g_raw + c * kTile * 4, src + (size_t)c * HW, row_bytes, full);
   };
 
-  uint32_t full_phase[2] = {0, 0}, mma_phase = 0;
-  int64_t tile = blockIdx.x;
+  uint32_t full_phase = 0, mma_phase = 0;
+  const int64_t stride = (int64_t)gridDim.x * Lt::kGroups;
+  int64_t tile = (int64_t)blockIdx.x * Lt::kGroups + group;
   if (tid == 0 && use_map) tmap::prefetch_map(&feat_map);
-  if (tid == 0 && tile < n_tiles) issue_load(tile, 0);
-  int buf = 0;
-  for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
-    const int64_t next = tile + gridDim.x;
-    if (tid == 0 && next < n_tiles) issue_load(next, buf ^ 1);            // raw[buf^1] was consumed two iterations ago
+  if (gt == 0 && tile < n_tiles) issue_load(tile);
+  for (; tile < n_tiles; tile += stride) {
+    const int64_t next = tile + stride;
     const int64_t b = tile / tiles_per_b, p0 = (tile % tiles_per_b) * kTile;
     const int valid = (int)((HW - p0) < kTile ? (HW - p0) : kTile);
 
-    tc::mbar_wait_or_trap(&full[buf], full_phase[buf], &g_fold_barrier_timeouts);   // bounded: a pipeline bug traps instead of hanging or running on
-    full_phase[buf] ^= 1u;
+    tc::mbar_wait_or_trap(full, full_phase, &g_fold_barrier_timeouts);   // bounded: a pipeline bug traps instead of hanging or running on
+    full_phase ^= 1u;
+    if (Lt::kStage) {                      // the previous tile's row stores have read the staging rows (= the operand tiles)
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      group_sync();
+    }
     // ---- transpose + split: thread = pixel row ----
     {
-      const float* raw = reinterpret_cast<const float*>(smem + Lt::kOffRaw + buf * Lt::kRaw);
+      const float* raw = reinterpret_cast<const float*>(g_raw);
 #pragma unroll 4
       for (int kc = 0; kc < C / 4; ++kc) {
         float f[4], h[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          f[j] = tid < valid ? raw[(kc * 4 + j) * kTile + tid] : 0.0f;
+          f[j] = gt < valid ? raw[(kc * 4 + j) * kTile + gt] : 0.0f;
           h[j] = __uint_as_float(__float_as_uint(f[j]) & 0xffffe000u);
         }
-        *reinterpret_cast<float4*>(smem + Lt::kOffAhi + (kc * kTile + tid) * 16) = make_float4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<float4*>(smem + Lt::kOffAlo + (kc * kTile + tid) * 16) = make_float4(f[0] - h[0], f[1] - h[1], f[2] - h[2], f[3] - h[3]);
+        *reinterpret_cast<float4*>(g_ahi + (kc * kTile + gt) * 16) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(g_alo + (kc * kTile + gt) * 16) = make_float4(f[0] - h[0], f[1] - h[1], f[2] - h[2], f[3] - h[3]);
       }
     }
     tc::fence_proxy_async_smem();
     tc::tc_fence_before_sync();
-    __syncthreads();                       // operand tiles complete; the previous tile's accumulator has been read
-    if (tid == 0) {
+    group_sync();                          // operand tiles complete, the raw tile is consumed; the previous accumulator has been read
+    if (warp_u == 0 && tc::elect_one()) {  // converged warp, one elected lane: operands stay in uniform registers
+      if (next < n_tiles) issue_load(next);                              // lands under the MMAs and the epilogue
       tc::tc_fence_after_sync();
-      const uint32_t sb = tc::smem_u32(smem);
+      const uint32_t sb = tc::smem_u32(smem), sa = tc::smem_u32(g_ahi), sl = tc::smem_u32(g_alo);
 #pragma unroll
       for (int ks = 0; ks < C / 8; ++ks) {
-        const uint64_t ahi = tc::smem_desc_kmajor_noswizzle(sb + Lt::kOffAhi + ks * 2 * kTile * 16, kTile * 16, 128);
-        const uint64_t alo = tc::smem_desc_kmajor_noswizzle(sb + Lt::kOffAlo + ks * 2 * kTile * 16, kTile * 16, 128);
+        const uint64_t ahi = tc::smem_desc_kmajor_noswizzle(sa + ks * 2 * kTile * 16, kTile * 16, 128);
+        const uint64_t alo = tc::smem_desc_kmajor_noswizzle(sl + ks * 2 * kTile * 16, kTile * 16, 128);
         const uint64_t whi = tc::smem_desc_kmajor_noswizzle(sb + Lt::kOffWhi + ks * 2 * HD * 16, HD * 16, 128);
         const uint64_t wlo = tc::smem_desc_kmajor_noswizzle(sb + Lt::kOffWlo + ks * 2 * HD * 16, HD * 16, 128);
         tc::mma_tf32_ss(tmem, ahi, whi, idesc, ks > 0);
@@ -161,25 +175,35 @@ __global__ void __launch_bounds__(kThreads, 1) fold_tc_kernel(const float* __res
     tc::tc_fence_after_sync();
     // ---- epilogue: accumulator row + bias -> G ----
     {
-      float* dst = G + ((size_t)b * HW + p0 + tid) * HD;
+      float* dst = G + ((size_t)b * HW + p0 + gt) * HD;
+      unsigned char* stage = g_ahi + gt * Lt::kStageRow;
 #pragma unroll
       for (int c0 = 0; c0 < HD; c0 += 16) {
         uint32_t v[16];
         tc::tmem_ld_x16(t_lane + c0, v);
         tc::tmem_ld_wait();
-        if (tid < valid) {
+        if (gt < valid) {
 #pragma unroll
-          for (int e = 0; e < 16; e += 4)
-            *reinterpret_cast<float4*>(dst + c0 + e) =
-                make_float4(__uint_as_float(v[e]) + s_bias[c0 + e], __uint_as_float(v[e + 1]) + s_bias[c0 + e + 1],
-                            __uint_as_float(v[e + 2]) + s_bias[c0 + e + 2], __uint_as_float(v[e + 3]) + s_bias[c0 + e + 3]);
+          for (int e = 0; e < 16; e += 4) {
+            const float4 o = make_float4(__uint_as_float(v[e]) + s_bias[c0 + e], __uint_as_float(v[e + 1]) + s_bias[c0 + e + 1],
+                                         __uint_as_float(v[e + 2]) + s_bias[c0 + e + 2], __uint_as_float(v[e + 3]) + s_bias[c0 + e + 3]);
+            if (Lt::kStage) *reinterpret_cast<float4*>(stage + (c0 + e) * 4) = o;
+            else *reinterpret_cast<float4*>(dst + c0 + e) = o;
+          }
         }
+      }
+      if (Lt::kStage) {
+        tc::fence_proxy_async_smem();      // my row -> async proxy
+        if (gt < valid)
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(tc::smem_u32(stage)), "n"(HD * 4) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
     tc::tc_fence_before_sync();
   }
+  if (Lt::kStage) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // my row stores are complete before the CTA's shared memory goes away
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc<Lt::kTmemCols>(tmem);
+  if (tid < 32) tc::tmem_dealloc<Lt::kTmemCols>(*tmem_slot);
 }
 
 }  // namespace foldtc
@@ -199,12 +223,13 @@ static cudaError_t launch_fold_tc_t(const float* feat, int n, int64_t HW, const 
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t n_tiles = ((HW + foldtc::kTile - 1) / foldtc::kTile) * n;
-  const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+  const int64_t want = (n_tiles + Lt::kGroups - 1) / Lt::kGroups;
+  const int grid = (int)(want < sms ? want : sms);
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
   const char* rows = getenv("BTS_FOLD_TMA_ROWS");            // tests: force the row-copy loads
   const int use_map = !(rows && rows[0] == '1') && tmap::make_feature_map(&map, feat, n, C, HW, foldtc::kTile) ? 1 : 0;
-  kern<<<grid, foldtc::kThreads, Lt::kSmemBytes, stream>>>(feat, HW, n, w_in, ld, b_in, G, map, use_map);
+  kern<<<grid, Lt::kThreads, Lt::kSmemBytes, stream>>>(feat, HW, n, w_in, ld, b_in, G, map, use_map);
   return cudaGetLastError();
 }
 
