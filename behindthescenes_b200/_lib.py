@@ -10,7 +10,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libbts_b200.so")
 
 BTS_MAX_BLOCKS = 8
-ABI_VERSION = 10
+ABI_VERSION = 11
 _fp = C.POINTER(C.c_float)
 
 
@@ -89,6 +89,14 @@ EXPORTS = {
                                   C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bts_fold_features_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                         C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bts_sparse_fold_supported": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "bts_mark_tiles": (C.c_int, [C.POINTER(BtsScene), C.POINTER(BtsRenderCfg), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                 C.c_uint64, C.c_void_p, C.c_void_p]),
+    "bts_fold_features_sparse": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                           C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bts_zero_tiles": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "bts_fold_features_bwd_sparse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                               C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bts_patch_smooth_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_int32,
                                        C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "bts_patch_smooth_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_int32,

@@ -252,8 +252,11 @@ class BTSNet(nn.Module):
             keep.append(steps)
         return c, keep
 
-    def _scene_struct(self):
-        """Render-ready scene for the current encode()/scale/weights; rebuilt when any of them changed."""
+    def _scene_struct(self, sparse=False):
+        """Render-ready scene for the current encode()/scale/weights; rebuilt when any of them changed.
+        ``sparse=True`` (training): the folded map is allocated but NOT computed here -- ``_sparse_prepare`` folds the
+        64-pixel tiles each ray batch samples (bts_mark_tiles + bts_fold_features_sparse); the tile mask lives with the
+        scene."""
         if self.grid_f_features is None:
             raise RuntimeError("call encode() first")
         lib = _lib.load()
@@ -267,7 +270,8 @@ class BTSNet(nn.Module):
         b_p = self.mlp_coarse.lin_in.bias
         key = (self._encode_gen, self._scale, w_in._version, w_in.data_ptr(), b_p._version, feats._version, feats.data_ptr(),
                None if ef is None else (ef._version, ef.data_ptr()))
-        hit = self._scene_cache.get(("scene", self._scale))   # one slot per scale (multiscale rendering, trainer.py:220-242)
+        slot = ("sparse" if sparse else "scene", self._scale)  # one slot per scale (multiscale rendering, trainer.py:220-242)
+        hit = self._scene_cache.get(slot)
         if hit is not None and hit[0] == key:
             return hit[1], hit[2]
         dev = feats.device
@@ -279,14 +283,18 @@ class BTSNet(nn.Module):
         G = torch.empty((n, H, W, Hd), device=dev, dtype=torch.float32)
         g_empty = torch.empty((Hd,), device=dev, dtype=torch.float32) if ef is not None else None
         efd = _dev_f32(ef.detach()) if ef is not None else None
-        with _lib.on_device(dev):
-            rc = lib.bts_fold_features(f.data_ptr(), n, Cf, H, W, w.data_ptr(), w.shape[1], b_in.data_ptr(), Hd,
-                                       None if efd is None else efd.data_ptr(), G.data_ptr(),
-                                       None if g_empty is None else g_empty.data_ptr(), stream)
-        _lib.check(rc, "bts_fold_features")
+        mask = None
+        if sparse:
+            mask = torch.zeros((n * ((H * W + 63) // 64),), device=dev, dtype=torch.uint8)   # 0: no ray batch has needed the tile yet
+        else:
+            with _lib.on_device(dev):
+                rc = lib.bts_fold_features(f.data_ptr(), n, Cf, H, W, w.data_ptr(), w.shape[1], b_in.data_ptr(), Hd,
+                                           None if efd is None else efd.data_ptr(), G.data_ptr(),
+                                           None if g_empty is None else g_empty.data_ptr(), stream)
+            _lib.check(rc, "bts_fold_features")
         # operand-block copy of G for the band kernel (single-frame scenes: evaluation / novel-view rendering)
         G16 = g16_flags = None
-        if n == 1 and Hd == 64 and getattr(self, "band_copy", True):
+        if n == 1 and Hd == 64 and getattr(self, "band_copy", True) and not sparse:
             G16 = torch.empty((lib.bts_g16_bytes(n, H, W, Hd),), device=dev, dtype=torch.uint8)
             g16_flags = torch.empty((1,), device=dev, dtype=torch.int32)
             with _lib.on_device(dev):
@@ -312,9 +320,44 @@ class BTSNet(nn.Module):
         s.same_view_mask = int(getattr(self, "_same_view_mask", 0)) if (Hc, Wc) == (H, W) else 0
         s.G16 = None if G16 is None else G16.data_ptr()
         s.g16_flags = None if g16_flags is None else g16_flags.data_ptr()
-        keep = [f, w, b_in, G, g_empty, efd, imgs, img4, Kf, Mf, Kc, Mc, G16, g16_flags]
-        self._scene_cache[("scene", self._scale)] = (key, s, keep)
+        keep = [f, w, b_in, G, g_empty, efd, imgs, img4, Kf, Mf, Kc, Mc, G16, g16_flags, mask]
+        if sparse:
+            s._sparse = dict(mask=mask, f=f, w=w, b_in=b_in, efd=efd, G=G, g_empty=g_empty, dims=(n, Cf, H, W, Hd))
+        self._scene_cache[slot] = (key, s, keep)
         return s, keep
+
+    def _sparse_ok(self, feats):
+        """Sparse fold (training) applies when the tensor-core fold kernels take the shape and alignment of this map."""
+        if not getattr(self, "sparse_fold", True) or feats is None or not feats.is_cuda:
+            return False
+        n, nv, Cf, H, W = feats.shape
+        ok = nv == 1 and feats.dtype == torch.float32 and feats.is_contiguous() and feats.data_ptr() % 16 == 0
+        return bool(ok and _lib.load().bts_sparse_fold_supported(Cf, H, W, self.mlp_coarse.d_hidden))
+
+    def _sparse_prepare(self, renderer, rays, u, seed):
+        """Fold the tiles of the current scale's map that this ray batch samples (and that no earlier batch of this
+        encode() has folded): bts_mark_tiles runs the renderers' own sampling / projection / tap code."""
+        import ctypes as C
+        lib = _lib.load()
+        scene, keep = self._scene_struct(sparse=True)
+        st = scene._sparse
+        cfg, keep3 = self._cfg_struct(renderer)
+        rays_d = _dev_f32(rays)
+        n, R, _ = rays_d.shape
+        dev = rays_d.device
+        u_d = _dev_f32(u.to(dev)) if u is not None else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        nb, Cf, H, W, Hd = st["dims"]
+        with _lib.on_device(dev):
+            rc = lib.bts_mark_tiles(C.byref(scene), C.byref(cfg), rays_d.data_ptr(), n, R,
+                                    None if u_d is None else u_d.data_ptr(), int(seed) & (2 ** 64 - 1), st["mask"].data_ptr(), stream)
+            _lib.check(rc, "bts_mark_tiles")
+            rc = lib.bts_fold_features_sparse(st["f"].data_ptr(), nb, Cf, H, W, st["w"].data_ptr(), st["w"].shape[1],
+                                              st["b_in"].data_ptr(), Hd, None if st["efd"] is None else st["efd"].data_ptr(),
+                                              st["G"].data_ptr(), None if st["g_empty"] is None else st["g_empty"].data_ptr(),
+                                              st["mask"].data_ptr(), stream)
+            _lib.check(rc, "bts_fold_features_sparse")
+        return scene, keep
 
     def render_rays(self, renderer, rays, u=None, seed=0, want_weights=False, want_alphas=False, want_z_samps=False,
                     want_rgb_samps=False, **extras):
@@ -360,11 +403,11 @@ class BTSNet(nn.Module):
 
     def _render_rays_raw(self, renderer, rays, u=None, seed=0, want_weights=False, want_alphas=False, want_z_samps=False,
                          want_rgb_samps=False, want_invalid=True, want_invalid_mass=False, want_depth_z=False, gen=None,
-                         want_sigma=False):
+                         want_sigma=False, sparse=False):
         """``rays`` (n,R,8), or ``rays=None`` with ``gen = (poses_c2w (n,v,4,4), Ks (n,v,3,3), H, W, z_near, z_far,
         norm_dir)`` to generate one ray per pixel of every view inside the kernel (bts_render_views_fwd)."""
         lib = _lib.load()
-        scene, keep = self._scene_struct()
+        scene, keep = self._sparse_prepare(renderer, rays, u, seed) if sparse else self._scene_struct()
         mlp, keep2 = self._mlp_struct()
         cfg, keep3 = self._cfg_struct(renderer)
         if gen is None:
@@ -436,11 +479,14 @@ class _RenderFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, renderer, rays, u, seed, wants, keys, feats, w_in, b_in, w_out, b_out, empty, fc0_w, fc0_b, fc1_w, fc1_b):
         with torch.no_grad():
-            out = net._render_rays_raw(renderer, rays, u=u, seed=seed, want_sigma=True, **wants)
+            # training folds only the tiles of the map this batch samples (sparse fold), when the shape allows
+            sparse = net._sparse_ok(feats)
+            out = net._render_rays_raw(renderer, rays, u=u, seed=seed, want_sigma=True, sparse=sparse, **wants)
             # the scene this forward rendered (folded map of the current scale, cameras, colour views): the backward must
             # scatter into / recompute against exactly this one, whatever set_scale() / encode() did in between
             # (multiscale training renders scales 0..3 before one loss.backward(), trainer.py:220-242)
-            ctx.scene, ctx.scene_keep = net._scene_struct()
+            ctx.scene, ctx.scene_keep = net._scene_struct(sparse=sparse)
+            ctx.tile_mask = ctx.scene._sparse["mask"] if sparse else None
         ctx.net, ctx.renderer, ctx.seed, ctx.keys = net, renderer, seed, keys
         ctx.sigma = out.pop("sigma")
         ctx.has_u = u is not None
@@ -475,7 +521,14 @@ class _RenderFunction(torch.autograd.Function):
                 g = _dev_f32(g)
                 held.append(g)
                 setattr(up, name, g.data_ptr())
-        dG = torch.zeros((scene.n, scene.H, scene.W, Hd), device=dev, dtype=torch.float32)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if ctx.tile_mask is not None:      # only the tiles the forward sampled receive gradient: zero those rows, leave the rest
+            dG = torch.empty((scene.n, scene.H, scene.W, Hd), device=dev, dtype=torch.float32)
+            with _lib.on_device(dev):
+                rc = lib.bts_zero_tiles(dG.data_ptr(), scene.n, scene.H, scene.W, Hd, ctx.tile_mask.data_ptr(), stream)
+            _lib.check(rc, "bts_zero_tiles")
+        else:
+            dG = torch.zeros((scene.n, scene.H, scene.W, Hd), device=dev, dtype=torch.float32)
         # every small accumulator lives in one zero-filled buffer (one launch instead of nine)
         sizes = [Hd, Hd * P, Hd, 1, Hd * Cf, Hd] + ([Hd * Hd, Hd, Hd * Hd, Hd] if ctx.has_block else [])
         flat = torch.zeros((sum(sizes),), device=dev, dtype=torch.float32)
@@ -507,8 +560,13 @@ class _RenderFunction(torch.autograd.Function):
         d_feats = torch.empty_like(feats_c) if need_df else None
         d_WF, d_b = d_WF_acc, d_b_acc
         with _lib.on_device(dev):
-            rc = lib.bts_fold_features_bwd(dG.data_ptr(), feats_c.data_ptr(), nb, Cf, H, W, w_c.data_ptr(), w_c.stride(0), Hd,
-                                           d_feats.data_ptr() if need_df else None, d_WF.data_ptr(), d_b.data_ptr(), stream)
+            if ctx.tile_mask is not None:
+                rc = lib.bts_fold_features_bwd_sparse(dG.data_ptr(), feats_c.data_ptr(), nb, Cf, H, W, w_c.data_ptr(), w_c.stride(0), Hd,
+                                                      d_feats.data_ptr() if need_df else None, d_WF.data_ptr(), d_b.data_ptr(),
+                                                      ctx.tile_mask.data_ptr(), stream)
+            else:
+                rc = lib.bts_fold_features_bwd(dG.data_ptr(), feats_c.data_ptr(), nb, Cf, H, W, w_c.data_ptr(), w_c.stride(0), Hd,
+                                               d_feats.data_ptr() if need_df else None, d_WF.data_ptr(), d_b.data_ptr(), stream)
         _lib.check(rc, "bts_fold_features_bwd")        # tensor-core kernel, or the CUDA-core one for odd shapes: no torch fallback
         d_b_in = d_b + dge
         if d_feats is not None and d_feats.dtype != feats.dtype:

@@ -10,8 +10,11 @@
 namespace bts {
 cudaError_t launch_general(const KernelParams& p, bool points, cudaStream_t stream);
 size_t general_smem_bytes(int Hd, int p_pad, int n_blocks);
+cudaError_t launch_mark_tiles(const KernelParams& p, unsigned char* mask, cudaStream_t stream);
+cudaError_t launch_zero_tiles(float* dG, int n, int64_t HW, int Hd, const unsigned char* mask, cudaStream_t stream);
+bool fold_tc_supported(const float* feat, int C, int64_t HW, int Hd);
 cudaError_t launch_fold(const float* feat, int n, int C, int H, int W, const float* w_in, int ld, const float* b_in, int Hd,
-                        const float* empty, float* G, float* g_empty, cudaStream_t stream);
+                        const float* empty, float* G, float* g_empty, unsigned char* tile_mask, cudaStream_t stream);
 cudaError_t launch_bwd(const BwdParams& bp, cudaStream_t stream, bool* used_tc);
 int bwd_tc_barrier_timeouts();
 size_t bwd_smem_bytes(int Hd, int p_pad, int K, int n_blocks);
@@ -22,7 +25,7 @@ int fold_barrier_timeouts();
 int fold_bwd_barrier_timeouts();
 bool fold_bwd_tc_supported(const float* dG, const float* feat, const float* d_feat, int C, int64_t HW, int Hd);
 cudaError_t launch_fold_bwd_tc(const float* dG, const float* feat, int n, int C, int64_t HW, const float* w_in, int ld, int Hd,
-                               float* d_feat, float* d_wf, float* d_b, cudaStream_t stream);
+                               float* d_feat, float* d_wf, float* d_b, const unsigned char* tile_mask, cudaStream_t stream);
 cudaError_t launch_patch_loss(const PatchLossParams& p, bool backward, cudaStream_t stream);
 bool patch_loss_supported(int h, int w, int nv, int c);
 cudaError_t launch_patch_smooth(const PatchLossParams& p, bool backward, cudaStream_t stream);
@@ -102,8 +105,67 @@ int bts_fold_features(const float* feat_nchw, int32_t n, int32_t C, int32_t H, i
   if (n < 1 || C < 1 || H < 1 || W < 1 || ld_w_in < C) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_fold_features: bad sizes");
   if (Hd % 32 != 0 || Hd < 32 || Hd > 128) return fail(BTS_ERR_UNSUPPORTED, "d_hidden=%d must be 32/64/96/128", Hd);
   const cudaError_t e = bts::launch_fold(feat_nchw, n, C, H, W, w_in, ld_w_in, b_in, Hd, empty_feature_or_null, G_out,
-                                         g_empty_out_or_null, reinterpret_cast<cudaStream_t>(stream));
+                                         g_empty_out_or_null, nullptr, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_fold_features: %s", cudaGetErrorString(e));
+  return BTS_OK;
+}
+
+// ---- sparse fold (training) -----------------------------------------------------------------------------------------
+int bts_sparse_fold_supported(int32_t C, int32_t H, int32_t W, int32_t Hd) {
+  const int64_t HW = (int64_t)H * W;
+  return (bts::fold_tc_supported(nullptr, C, HW, Hd) && bts::fold_bwd_tc_supported(nullptr, nullptr, nullptr, C, HW, Hd)) ? 1 : 0;
+}
+
+int bts_mark_tiles(const BtsScene* scene, const BtsRenderCfg* cfg, const float* rays, int64_t n, int64_t R,
+                   const float* u_or_null, uint64_t seed, uint8_t* tile_mask, bts_stream_t stream) {
+  if (!scene || !cfg || !rays || !tile_mask) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_mark_tiles: null pointer");
+  if (!scene->K_f || !scene->w2c_f || scene->n < 1 || scene->H < 1 || scene->W < 1)
+    return fail(BTS_ERR_INVALID_ARGUMENT, "bts_mark_tiles: scene needs n, H, W, K_f, w2c_f");
+  if (n != scene->n) return fail(BTS_ERR_INVALID_ARGUMENT, "rays batch %lld != scene.n %d", (long long)n, scene->n);
+  if (cfg->n_coarse < 1 || !cfg->z_steps) return fail(BTS_ERR_INVALID_ARGUMENT, "n_coarse < 1 or z_steps null");
+  if (n * R <= 0) return BTS_OK;
+  bts::KernelParams p;
+  memset(&p, 0, sizeof(p));
+  p.scene = *scene; p.cfg = *cfg;
+  p.rays = rays; p.u = u_or_null; p.n_items = n * R; p.per_batch = R; p.seed = seed;
+  const cudaError_t e = bts::launch_mark_tiles(p, tile_mask, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_mark_tiles: %s", cudaGetErrorString(e));
+  return BTS_OK;
+}
+
+int bts_fold_features_sparse(const float* feat_nchw, int32_t n, int32_t C, int32_t H, int32_t W, const float* w_in,
+                             int32_t ld_w_in, const float* b_in, int32_t Hd, const float* empty_feature_or_null,
+                             float* G_out, float* g_empty_out_or_null, uint8_t* tile_mask, bts_stream_t stream) {
+  if (!feat_nchw || !w_in || !b_in || !G_out || !tile_mask) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_fold_features_sparse: null pointer");
+  if (n < 1 || C < 1 || H < 1 || W < 1 || ld_w_in < C) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_fold_features_sparse: bad sizes");
+  if (!bts::fold_tc_supported(feat_nchw, C, (int64_t)H * W, Hd))
+    return fail(BTS_ERR_UNSUPPORTED, "bts_fold_features_sparse: shape / alignment outside the tensor-core fold (see bts_sparse_fold_supported)");
+  const cudaError_t e = bts::launch_fold(feat_nchw, n, C, H, W, w_in, ld_w_in, b_in, Hd, empty_feature_or_null, G_out,
+                                         g_empty_out_or_null, tile_mask, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_fold_features_sparse: %s", cudaGetErrorString(e));
+  return BTS_OK;
+}
+
+int bts_zero_tiles(float* d_G, int32_t n, int32_t H, int32_t W, int32_t Hd, const uint8_t* tile_mask, bts_stream_t stream) {
+  if (!d_G || !tile_mask) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_zero_tiles: null pointer");
+  if (n < 1 || H < 1 || W < 1 || Hd < 4 || Hd % 4 != 0 || (reinterpret_cast<uintptr_t>(d_G) & 15) != 0)
+    return fail(BTS_ERR_INVALID_ARGUMENT, "bts_zero_tiles: bad sizes / alignment");
+  const cudaError_t e = bts::launch_zero_tiles(d_G, n, (int64_t)H * W, Hd, tile_mask, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_zero_tiles: %s", cudaGetErrorString(e));
+  return BTS_OK;
+}
+
+int bts_fold_features_bwd_sparse(const float* d_G, const float* feat_nchw, int32_t n, int32_t C, int32_t H, int32_t W,
+                                 const float* w_in, int32_t ld, int32_t Hd, float* d_feat_or_null, float* d_w_f,
+                                 float* d_b_in, const uint8_t* tile_mask, bts_stream_t stream) {
+  if (!d_G || !feat_nchw || !w_in || !d_w_f || !d_b_in || !tile_mask) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_fold_features_bwd_sparse: null pointer");
+  if (n < 1 || C < 1 || H < 1 || W < 1 || Hd < 1 || ld < C) return fail(BTS_ERR_INVALID_ARGUMENT, "bts_fold_features_bwd_sparse: bad sizes");
+  const int64_t HW = (int64_t)H * W;
+  if (!bts::fold_bwd_tc_supported(d_G, feat_nchw, d_feat_or_null, C, HW, Hd))
+    return fail(BTS_ERR_UNSUPPORTED, "bts_fold_features_bwd_sparse: shape / alignment outside the tensor-core fold (see bts_sparse_fold_supported)");
+  const cudaError_t e = bts::launch_fold_bwd_tc(d_G, feat_nchw, n, C, HW, w_in, ld, Hd, d_feat_or_null, d_w_f, d_b_in, tile_mask,
+                                                reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_fold_features_bwd_sparse: %s", cudaGetErrorString(e));
   return BTS_OK;
 }
 
@@ -243,7 +305,7 @@ int bts_fold_features_bwd(const float* d_G, const float* feat_nchw, int32_t n, i
   const int64_t HW = (int64_t)H * W;
   cudaError_t e;
   if (bts::fold_bwd_tc_supported(d_G, feat_nchw, d_feat_or_null, C, HW, Hd))      // TMA-fed tcgen05 kernel
-    e = bts::launch_fold_bwd_tc(d_G, feat_nchw, n, C, HW, w_in, ld, Hd, d_feat_or_null, d_w_f, d_b_in, reinterpret_cast<cudaStream_t>(stream));
+    e = bts::launch_fold_bwd_tc(d_G, feat_nchw, n, C, HW, w_in, ld, Hd, d_feat_or_null, d_w_f, d_b_in, nullptr, reinterpret_cast<cudaStream_t>(stream));
   else                                                                               // any other shape: CUDA-core kernel
     e = bts::launch_fold_bwd_simt(d_G, feat_nchw, n, C, HW, w_in, ld, Hd, d_feat_or_null, d_w_f, d_b_in, reinterpret_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(BTS_ERR_CUDA, "bts_fold_features_bwd: %s", cudaGetErrorString(e));

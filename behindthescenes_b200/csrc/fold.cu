@@ -93,22 +93,86 @@ __global__ void pack_images_kernel(const float* __restrict__ img, int Cc, int64_
 
 bool fold_tc_supported(const float* feat, int C, int64_t HW, int Hd);
 cudaError_t launch_fold_tc(const float* feat, int n, int C, int64_t HW, const float* w_in, int ld, const float* b_in, int Hd,
-                           float* G, cudaStream_t stream);
+                           float* G, unsigned char* tile_mask, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------------------------
+// Sparse fold (training path).  A training batch samples the folded map along the epipolar lines of a few 8x8 patches
+// (models/bts/model/ray_sampler.py: PatchRaySampler): ~15-25 % of a frame's 64-pixel tiles.  mark_tiles_kernel runs the
+// renderers' sampling + projection (the same device functions, so exactly the same taps) and flags the tiles a ray
+// batch reads; the fold kernels then produce / differentiate only those.  Mask byte per 64 pixels of a frame:
+// 0 = nothing reads it, 1 = needed, 2 = folded.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mark_tiles_kernel(const KernelParams p, unsigned char* __restrict__ mask, int mask_per_b) {
+  const int lane = threadIdx.x & 31, K = p.cfg.n_coarse, H = p.scene.H, W = p.scene.W;
+  const bool use_empty = p.cfg.learn_empty && p.scene.g_empty != nullptr;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ray < p.n_items; ray += warps) {
+    const int64_t b = p.scene.n == 1 ? 0 : ray / p.per_batch;
+    const Ray ry = fetch_ray(p, ray, lane);
+    float near_, far_;
+    depth_bounds(p, ry, near_, far_);
+    View vf;
+    load_view(vf, p.scene.K_f + b * 9, p.scene.w2c_f + b * 16);
+    unsigned char* m = mask + b * mask_per_b;
+    for (int k = lane; k < K; k += 32) {
+      const float z = sample_depth(p, ray, k, near_, far_);
+      const Proj pf = project(vf, __fadd_rn(ry.o[0], __fmul_rn(z, ry.d[0])), __fadd_rn(ry.o[1], __fmul_rn(z, ry.d[1])),
+                              __fadd_rn(ry.o[2], __fmul_rn(z, ry.d[2])));
+      if (use_empty && pf.invalid) continue;          // takes the learned empty row: no fetch
+      const Taps t = bilinear_taps(pf.u, pf.v, H, W);
+      const int p00 = t.y0 * W + t.x0, p10 = p00 + t.dy * W;
+      const int tiles[4] = {p00 >> 6, (p00 + t.dx) >> 6, p10 >> 6, (p10 + t.dx) >> 6};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (m[tiles[i]] == 0) m[tiles[i]] = 1;        // benign race: every writer stores 1
+    }
+  }
+}
+
+cudaError_t launch_mark_tiles(const KernelParams& p, unsigned char* mask, cudaStream_t stream) {
+  const int64_t HW = (int64_t)p.scene.H * p.scene.W;
+  const int64_t want = (p.n_items + 7) / 8;
+  mark_tiles_kernel<<<(unsigned)(want < 1184 ? (want > 0 ? want : 1) : 1184), 256, 0, stream>>>(p, mask, (int)((HW + 63) / 64));
+  return cudaGetLastError();
+}
+
+// Zero the rows of d_G (n, HW, Hd) that belong to marked tiles: the render backward accumulates into exactly those.
+__global__ void __launch_bounds__(256) zero_tiles_kernel(float4* __restrict__ dG, int64_t HW, int Hd, int mask_per_b, int64_t n_tiles,
+                                                         const unsigned char* __restrict__ mask) {
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    if (mask[t] == 0) continue;
+    const int64_t b = t / mask_per_b, j = t % mask_per_b;
+    const int64_t px = HW - j * 64 < 64 ? HW - j * 64 : 64;
+    float4* dst = dG + ((b * HW + j * 64) * Hd) / 4;
+    for (int i = threadIdx.x; i < px * Hd / 4; i += blockDim.x) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+cudaError_t launch_zero_tiles(float* dG, int n, int64_t HW, int Hd, const unsigned char* mask, cudaStream_t stream) {
+  const int mask_per_b = (int)((HW + 63) / 64);
+  const int64_t n_tiles = (int64_t)mask_per_b * n;
+  zero_tiles_kernel<<<(unsigned)(n_tiles < 4736 ? n_tiles : 4736), 256, 0, stream>>>(reinterpret_cast<float4*>(dG), HW, Hd, mask_per_b, n_tiles, mask);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_fold(const float* feat, int n, int C, int H, int W, const float* w_in, int ld, const float* b_in, int Hd,
-                        const float* empty, float* G, float* g_empty, cudaStream_t stream) {
+                        const float* empty, float* G, float* g_empty, unsigned char* tile_mask, cudaStream_t stream) {
   const int64_t HW = (int64_t)H * W;
   // tensor-core path (TMA-fed tcgen05 GEMM, fold_tc.cu) whenever the frame qualifies; BTS_FOLD_SIMT=1 forces the
   // CUDA-core kernel (tests compare the two)
   static const bool force_simt = [] { const char* v = getenv("BTS_FOLD_SIMT"); return v && v[0] == '1'; }();   // read once
   if (!force_simt && fold_tc_supported(feat, C, HW, Hd)) {
-    cudaError_t e = launch_fold_tc(feat, n, C, HW, w_in, ld, b_in, Hd, G, stream);
+    cudaError_t e = launch_fold_tc(feat, n, C, HW, w_in, ld, b_in, Hd, G, tile_mask, stream);
     if (e != cudaSuccess) return e;
     if (empty && g_empty) {
       fold_empty_kernel<<<(Hd + 127) / 128, 128, 0, stream>>>(empty, C, w_in, ld, Hd, b_in, g_empty);
       e = cudaGetLastError();
     }
     return e;
+  }
+  if (tile_mask) {    // the CUDA-core kernel folds the whole map: every tile is valid afterwards
+    cudaError_t em = cudaMemsetAsync(tile_mask, 2, (size_t)((HW + 63) / 64) * n, stream);
+    if (em != cudaSuccess) return em;
   }
   dim3 grid((unsigned)((HW + kFoldPix - 1) / kFoldPix), (unsigned)n);
   switch (Hd / 8) {

@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(kThreads, 1) fold_bwd_tc_kernel(const float* _
                                                                    int64_t HW, int n_batches, const float* __restrict__ w_in,
                                                                    int ld, float* __restrict__ d_feat, float* __restrict__ d_wf,
                                                                    float* __restrict__ d_b,
-                                                                   const __grid_constant__ CUtensorMap feat_map, int use_map) {
+                                                                   const __grid_constant__ CUtensorMap feat_map, int use_map,
+                                                                   const unsigned char* __restrict__ tile_mask) {
   using Lt = L<HD, C>;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -141,15 +142,32 @@ __global__ void __launch_bounds__(kThreads, 1) fold_bwd_tc_kernel(const float* _
   };
 
   uint32_t full_phase[2] = {0, 0}, mma_phase = 0;
-  int64_t tile = blockIdx.x;
+  // Sparse fold (training): tile_mask has one byte per 64-pixel tile, 0 = no ray of the batch sampled it -- its d_G rows were
+  // never written (and not even zeroed): the tile contributes nothing to dW_F / db_in and its dF rows are zeros.
+  auto zero_tile = [&](int64_t t) {
+    if (!want_df) return;
+    const int64_t b = t / tiles_per_b, p0 = (t % tiles_per_b) * kTile;
+    const int valid = (int)((HW - p0) < kTile ? (HW - p0) : kTile);
+    float* dst = d_feat + ((size_t)b * C) * HW + p0;
+    for (int i = tid; i < C * (kTile / 4); i += kThreads) {
+      const int c = i / (kTile / 4), seg = i % (kTile / 4);
+      if (seg * 4 < valid) *reinterpret_cast<float4*>(dst + (size_t)c * HW + seg * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto advance = [&](int64_t t) {                          // next tile of this CTA that carries gradient; the others get zeros
+    while (t < n_tiles && tile_mask && tile_mask[t] == 0) { zero_tile(t); t += gridDim.x; }
+    return t;
+  };
+  int64_t tile = advance(blockIdx.x);
   if (tid == 0 && use_map) tmap::prefetch_map(&feat_map);
   if (tid == 0 && tile < n_tiles) issue_load(tile, 0);
   int buf = 0;
   bool first = true;
   float* ex = reinterpret_cast<float*>(smem + Lt::kOffEx);
   constexpr int kExF = kTile + kPad;
-  for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
-    const int64_t next = tile + gridDim.x;
+  int64_t next;
+  for (; tile < n_tiles; tile = next, buf ^= 1) {
+    next = advance(tile + gridDim.x);
     if (tid == 0 && next < n_tiles) issue_load(next, buf ^ 1);             // raw[buf^1] was consumed one iteration ago
     const int64_t b = tile / tiles_per_b, p0 = (tile % tiles_per_b) * kTile;
     const int valid = (int)((HW - p0) < kTile ? (HW - p0) : kTile);
@@ -275,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) fold_bwd_tc_kernel(const float* _
   // ---- final: dW_F[k, :] and db_in[k] from D2 rows k and 64 + k ----
   __syncthreads();
   tc::tc_fence_after_sync();
-  {
+  if (!first) {                            // a CTA whose tiles were all skipped never wrote its accumulator
     float row[Lt::kN2];
     if (warp < 4) {
 #pragma unroll
@@ -314,7 +332,7 @@ bool fold_bwd_tc_supported(const float* dG, const float* feat, const float* d_fe
 
 template <int HD, int C>
 static cudaError_t launch_fold_bwd_t(const float* dG, const float* feat, int n, int64_t HW, const float* w_in, int ld,
-                                     float* d_feat, float* d_wf, float* d_b, cudaStream_t stream) {
+                                     float* d_feat, float* d_wf, float* d_b, const unsigned char* tile_mask, cudaStream_t stream) {
   using Lt = foldbwd::L<HD, C>;
   auto kern = foldbwd::fold_bwd_tc_kernel<HD, C>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Lt::kSmemBytes);
@@ -328,16 +346,16 @@ static cudaError_t launch_fold_bwd_t(const float* dG, const float* feat, int n, 
   memset(&map, 0, sizeof(map));
   const char* rows = getenv("BTS_FOLD_TMA_ROWS");            // tests: force the row-copy loads
   const int use_map = !(rows && rows[0] == '1') && tmap::make_feature_map(&map, feat, n, C, HW, foldbwd::kTile) ? 1 : 0;
-  kern<<<grid, foldbwd::kThreads, Lt::kSmemBytes, stream>>>(dG, feat, HW, n, w_in, ld, d_feat, d_wf, d_b, map, use_map);
+  kern<<<grid, foldbwd::kThreads, Lt::kSmemBytes, stream>>>(dG, feat, HW, n, w_in, ld, d_feat, d_wf, d_b, map, use_map, tile_mask);
   return cudaGetLastError();
 }
 
 cudaError_t launch_fold_bwd_tc(const float* dG, const float* feat, int n, int C, int64_t HW, const float* w_in, int ld, int Hd,
-                               float* d_feat, float* d_wf, float* d_b, cudaStream_t stream) {
-  if (C == 64 && Hd == 64) return launch_fold_bwd_t<64, 64>(dG, feat, n, HW, w_in, ld, d_feat, d_wf, d_b, stream);
-  if (C == 64 && Hd == 32) return launch_fold_bwd_t<32, 64>(dG, feat, n, HW, w_in, ld, d_feat, d_wf, d_b, stream);
-  if (C == 32 && Hd == 64) return launch_fold_bwd_t<64, 32>(dG, feat, n, HW, w_in, ld, d_feat, d_wf, d_b, stream);
-  if (C == 32 && Hd == 32) return launch_fold_bwd_t<32, 32>(dG, feat, n, HW, w_in, ld, d_feat, d_wf, d_b, stream);
+                               float* d_feat, float* d_wf, float* d_b, const unsigned char* tile_mask, cudaStream_t stream) {
+  if (C == 64 && Hd == 64) return launch_fold_bwd_t<64, 64>(dG, feat, n, HW, w_in, ld, d_feat, d_wf, d_b, tile_mask, stream);
+  if (C == 64 && Hd == 32) return launch_fold_bwd_t<32, 64>(dG, feat, n, HW, w_in, ld, d_feat, d_wf, d_b, tile_mask, stream);
+  if (C == 32 && Hd == 64) return launch_fold_bwd_t<64, 32>(dG, feat, n, HW, w_in, ld, d_feat, d_wf, d_b, tile_mask, stream);
+  if (C == 32 && Hd == 32) return launch_fold_bwd_t<32, 32>(dG, feat, n, HW, w_in, ld, d_feat, d_wf, d_b, tile_mask, stream);
   return cudaErrorInvalidValue;
 }
 

@@ -64,7 +64,8 @@ template <int HD, int C>
 __global__ void __launch_bounds__(L<HD, C>::kThreads, 1) fold_tc_kernel(const float* __restrict__ feat, int64_t HW, int n_batches,
                                                                         const float* __restrict__ w_in, int ld,
                                                                         const float* __restrict__ b_in, float* __restrict__ G,
-                                                                        const __grid_constant__ CUtensorMap feat_map, int use_map) {
+                                                                        const __grid_constant__ CUtensorMap feat_map, int use_map,
+                                                                        unsigned char* __restrict__ tile_mask, int mask_per_b) {
   using Lt = L<HD, C>;
   constexpr int kThreads = Lt::kThreads;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -121,11 +122,24 @@ __global__ void __launch_bounds__(L<HD, C>::kThreads, 1) fold_tc_kernel(const fl
 
   uint32_t full_phase = 0, mma_phase = 0;
   const int64_t stride = (int64_t)gridDim.x * Lt::kGroups;
-  int64_t tile = (int64_t)blockIdx.x * Lt::kGroups + group;
+  // Sparse fold (training): tile_mask has one byte per 64 pixels of a frame -- 0 nothing samples it, 1 needed, 2 folded
+  // already; a 128-pixel tile is produced when one of its halves is needed, and both halves are then marked folded.
+  auto mask_of = [&](int64_t t) { return tile_mask + (t / tiles_per_b) * mask_per_b + (t % tiles_per_b) * 2; };
+  auto needed = [&](int64_t t) {
+    if (!tile_mask) return true;
+    const unsigned char* m = mask_of(t);
+    return m[0] == 1 || ((t % tiles_per_b) * 2 + 1 < mask_per_b && m[1] == 1);
+  };
+  auto advance = [&](int64_t t) {                         // first tile of this group at or after t that has to be folded
+    while (t < n_tiles && !needed(t)) t += stride;
+    return t;
+  };
+  int64_t tile = advance((int64_t)blockIdx.x * Lt::kGroups + group);
   if (tid == 0 && use_map) tmap::prefetch_map(&feat_map);
   if (gt == 0 && tile < n_tiles) issue_load(tile);
-  for (; tile < n_tiles; tile += stride) {
-    const int64_t next = tile + stride;
+  int64_t next;
+  for (; tile < n_tiles; tile = next) {
+    next = advance(tile + stride);
     const int64_t b = tile / tiles_per_b, p0 = (tile % tiles_per_b) * kTile;
     const int valid = (int)((HW - p0) < kTile ? (HW - p0) : kTile);
 
@@ -198,6 +212,11 @@ __global__ void __launch_bounds__(L<HD, C>::kThreads, 1) fold_tc_kernel(const fl
           asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(tc::smem_u32(stage)), "n"(HD * 4) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
+      if (tile_mask && gt == 0) {
+        unsigned char* m = mask_of(tile);
+        m[0] = 2;
+        if ((tile % tiles_per_b) * 2 + 1 < mask_per_b) m[1] = 2;
+      }
     }
     tc::tc_fence_before_sync();
   }
@@ -214,7 +233,7 @@ bool fold_tc_supported(const float* feat, int C, int64_t HW, int Hd) {
 
 template <int HD, int C>
 static cudaError_t launch_fold_tc_t(const float* feat, int n, int64_t HW, const float* w_in, int ld, const float* b_in, float* G,
-                                    cudaStream_t stream) {
+                                    unsigned char* tile_mask, cudaStream_t stream) {
   using Lt = foldtc::L<HD, C>;
   auto kern = foldtc::fold_tc_kernel<HD, C>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Lt::kSmemBytes);
@@ -229,20 +248,20 @@ static cudaError_t launch_fold_tc_t(const float* feat, int n, int64_t HW, const 
   memset(&map, 0, sizeof(map));
   const char* rows = getenv("BTS_FOLD_TMA_ROWS");            // tests: force the row-copy loads
   const int use_map = !(rows && rows[0] == '1') && tmap::make_feature_map(&map, feat, n, C, HW, foldtc::kTile) ? 1 : 0;
-  kern<<<grid, Lt::kThreads, Lt::kSmemBytes, stream>>>(feat, HW, n, w_in, ld, b_in, G, map, use_map);
+  kern<<<grid, Lt::kThreads, Lt::kSmemBytes, stream>>>(feat, HW, n, w_in, ld, b_in, G, map, use_map, tile_mask, (int)((HW + 63) / 64));
   return cudaGetLastError();
 }
 
 cudaError_t launch_fold_tc(const float* feat, int n, int C, int64_t HW, const float* w_in, int ld, const float* b_in, int Hd,
-                           float* G, cudaStream_t stream) {
+                           float* G, unsigned char* tile_mask, cudaStream_t stream) {
   if (C == 64) {
-    if (Hd == 64) return launch_fold_tc_t<64, 64>(feat, n, HW, w_in, ld, b_in, G, stream);
-    if (Hd == 128) return launch_fold_tc_t<128, 64>(feat, n, HW, w_in, ld, b_in, G, stream);
-    if (Hd == 32) return launch_fold_tc_t<32, 64>(feat, n, HW, w_in, ld, b_in, G, stream);
+    if (Hd == 64) return launch_fold_tc_t<64, 64>(feat, n, HW, w_in, ld, b_in, G, tile_mask, stream);
+    if (Hd == 128) return launch_fold_tc_t<128, 64>(feat, n, HW, w_in, ld, b_in, G, tile_mask, stream);
+    if (Hd == 32) return launch_fold_tc_t<32, 64>(feat, n, HW, w_in, ld, b_in, G, tile_mask, stream);
   } else if (C == 32) {
-    if (Hd == 32) return launch_fold_tc_t<32, 32>(feat, n, HW, w_in, ld, b_in, G, stream);
-    if (Hd == 64) return launch_fold_tc_t<64, 32>(feat, n, HW, w_in, ld, b_in, G, stream);
-    if (Hd == 128) return launch_fold_tc_t<128, 32>(feat, n, HW, w_in, ld, b_in, G, stream);
+    if (Hd == 32) return launch_fold_tc_t<32, 32>(feat, n, HW, w_in, ld, b_in, G, tile_mask, stream);
+    if (Hd == 64) return launch_fold_tc_t<64, 32>(feat, n, HW, w_in, ld, b_in, G, tile_mask, stream);
+    if (Hd == 128) return launch_fold_tc_t<128, 32>(feat, n, HW, w_in, ld, b_in, G, tile_mask, stream);
   }
   return cudaErrorInvalidValue;
 }

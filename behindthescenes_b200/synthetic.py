@@ -154,6 +154,25 @@ def cfg3_kitti_raw_train(H=370, W=1226, K=64, n=1, seed=0, lin_out_bias=0.0, ray
                          lin_out_bias=lin_out_bias, ray_subsample=ray_subsample)
 
 
+def with_patch_rays(wl: Workload, H: int, W: int, n_views: int, patches: int, seed: int = 0, patch: int = 8) -> Workload:
+    """Replace the workload's rays by ``patches`` random ``patch`` x ``patch`` pixel patches per frame, drawn from its
+    ``n_views`` ray views -- what ``PatchRaySampler.sample`` hands the training step (models/bts/model/ray_sampler.py:108-160;
+    configs/exp_kitti_raw.yaml: patch_size 8, ray_batch_size 2048 = 32 patches), different per frame.  Ray order: patch-major,
+    row-major inside a patch (the layout ``PatchRaySampler.reconstruct`` views as (n, P, 8, 8))."""
+    n = wl.rays.shape[0]
+    g = torch.Generator().manual_seed(seed + 1234)
+    all_rays = wl.rays.view(n, n_views, H, W, 8)
+    sel = []
+    for b in range(n):
+        v = torch.randint(0, n_views, (patches,), generator=g).tolist()
+        y = torch.randint(0, H - patch + 1, (patches,), generator=g).tolist()
+        x = torch.randint(0, W - patch + 1, (patches,), generator=g).tolist()
+        sel.append(torch.cat([all_rays[b, v[i], y[i]:y[i] + patch, x[i]:x[i] + patch].reshape(patch * patch, 8) for i in range(patches)]))
+    wl.rays = torch.stack(sel).contiguous()
+    wl.u = torch.rand((n * patches * patch * patch, wl.renderer_conf["n_coarse"]), generator=g)
+    return wl
+
+
 def cfg4_re10k_nvs(H=256, W=384, K=128, seed=0, lin_out_bias=0.0, ray_subsample=None) -> Workload:
     """BASELINE config 4: RE10K shape, C=32, Hd=32, one ResNet block, distance code, novel pose, 2 colour views."""
     poses = [_pose(), _pose(tx=0.15, yaw_deg=-2.0), _pose(tx=-0.1, tz=0.2, yaw_deg=1.5)]

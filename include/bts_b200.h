@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define BTS_ABI_VERSION 10
+#define BTS_ABI_VERSION 11
 #define BTS_MAX_BLOCKS 8   /* ResnetFC blocks supported by the kernels */
 
 typedef struct CUstream_st* bts_stream_t; /* == cudaStream_t */
@@ -225,6 +225,30 @@ int bts_query_field(const BtsScene* scene, const BtsMlp* mlp, const BtsRenderCfg
 int bts_fold_features_bwd(const float* d_G, const float* feat_nchw, int32_t n, int32_t C, int32_t H, int32_t W,
                           const float* w_in, int32_t ld, int32_t Hd, float* d_feat_or_null, float* d_w_f, float* d_b_in,
                           bts_stream_t stream);
+
+/* Sparse fold, the training form of the encode-side glue.  A training batch (PatchRaySampler: 8x8 pixel patches,
+ * models/bts/model/ray_sampler.py:108-195) samples the folded map only along the epipolar lines of its patches, typically
+ * 15-25 % of a frame, while F.grid_sample of the reference (models_bts.py:179) reads -- and autograd differentiates -- only
+ * the sampled texels.  tile_mask holds one byte per 64 consecutive pixels of a frame (n * BTS_TILE_MASK_PER_FRAME(H, W)
+ * bytes; 0 = no ray reads it, 1 = needed, 2 = folded), zeroed by the caller once per encode() / weight update:
+ *   bts_mark_tiles            flags the tiles the taps of a ray batch fall into (the renderers' own sampling, projection and
+ *                             tap code: exactly the texels bts_render_fwd / bts_render_bwd will touch)
+ *   bts_fold_features_sparse  bts_fold_features for the tiles in state 1 only (-> state 2); G elsewhere stays undefined
+ *   bts_zero_tiles            zeroes the d_G rows of the tiles in state != 0 (instead of a memset of the whole tensor)
+ *   bts_fold_features_bwd_sparse  bts_fold_features_bwd over those tiles; d_feat rows of all other tiles are written as zeros
+ * bts_sparse_fold_supported: 1 when the tensor-core fold kernels take the shape (the sparse path has no CUDA-core form). */
+#define BTS_TILE_PIXELS 64
+#define BTS_TILE_MASK_PER_FRAME(H, W) (((int64_t)(H) * (W) + BTS_TILE_PIXELS - 1) / BTS_TILE_PIXELS)
+int bts_sparse_fold_supported(int32_t C, int32_t H, int32_t W, int32_t Hd);
+int bts_mark_tiles(const BtsScene* scene, const BtsRenderCfg* cfg, const float* rays, int64_t n, int64_t R,
+                   const float* u_or_null, uint64_t seed, uint8_t* tile_mask, bts_stream_t stream);
+int bts_fold_features_sparse(const float* feat_nchw, int32_t n, int32_t C, int32_t H, int32_t W, const float* w_in,
+                             int32_t ld_w_in, const float* b_in, int32_t Hd, const float* empty_feature_or_null,
+                             float* G_out, float* g_empty_out_or_null, uint8_t* tile_mask, bts_stream_t stream);
+int bts_zero_tiles(float* d_G, int32_t n, int32_t H, int32_t W, int32_t Hd, const uint8_t* tile_mask, bts_stream_t stream);
+int bts_fold_features_bwd_sparse(const float* d_G, const float* feat_nchw, int32_t n, int32_t C, int32_t H, int32_t W,
+                                 const float* w_in, int32_t ld, int32_t Hd, float* d_feat_or_null, float* d_w_f,
+                                 float* d_b_in, const uint8_t* tile_mask, bts_stream_t stream);
 
 /* Patch photometric loss of the training step: replaces compute_errors_l1ssim (models/bts/model/loss.py:10-18, SSIM of
  * models/common/model/layers.py:79-150 with zero padding, 3x3 gaussian window, comp_mode) and the reduction of

@@ -35,7 +35,7 @@ def test_every_declared_symbol_is_exported(lib):
     for n in _declared_functions():
         assert hasattr(lib, n), f"{n} declared in include/bts_b200.h but not exported"
         assert n in _lib.EXPORTS, f"{n} has no ctypes prototype"
-    assert lib.bts_abi_version() == 10
+    assert lib.bts_abi_version() == 11
     assert lib.bts_last_error() is not None
 
 

@@ -148,3 +148,72 @@ def test_row_copy_loads_agree_with_tensor_map_loads(monkeypatch):
     assert rc == 0 and _lib.load().bts_debug_tc_timeouts() == 0
     assert torch.equal(G_map, G_rows) and torch.equal(df_map, df_rows)
     assert torch.allclose(dwf_map, dwf_rows, rtol=1e-5, atol=1e-4) and torch.allclose(db_map, db_rows, rtol=1e-5, atol=1e-4)
+
+
+# ---- sparse fold (training): only the 64-pixel tiles a ray batch samples are folded / differentiated ---------------------
+
+def _patch_workload(H=48, W=160, n=2, patches=6, seed=5):
+    """cfg3-shaped training workload whose rays are real 8x8 pixel patches (PatchRaySampler), different per frame."""
+    from behindthescenes_b200 import synthetic as syn
+    wl = syn.cfg3_kitti_raw_train(H=H, W=W, n=n, lin_out_bias=-4.0, seed=seed)
+    return syn.with_patch_rays(wl, H, W, 2, patches, seed=seed)
+
+
+def test_sparse_fold_marks_and_folds_exactly_the_sampled_tiles():
+    """bts_mark_tiles + bts_fold_features_sparse: marked tiles equal the dense fold bit for bit, a superset of the tiles the
+    renderer's taps touch (checked through the render: sparse and dense outputs are identical), unmarked tiles untouched."""
+    import ctypes as C
+    from behindthescenes_b200 import synthetic as syn
+    wl = _patch_workload(H=96, W=320, patches=3)
+    net, wrapped = syn.build_model(wl, "cuda")
+    with torch.no_grad():
+        net.encode(wl.images.cuda(), wl.Ks.cuda(), wl.poses_c2w.cuda(), ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
+        feats = net.grid_f_features[0]
+        assert net._sparse_ok(feats)
+        rays, u = wl.rays.cuda(), wl.u.cuda()
+        dense = net._render_rays_raw(wrapped.renderer, rays, u=u, want_weights=True, want_alphas=True)
+        Gd = net._scene_struct()[1][3].clone()
+        sparse = net._render_rays_raw(wrapped.renderer, rays, u=u, want_weights=True, want_alphas=True, sparse=True)
+        scene, keep = net._scene_struct(sparse=True)
+        mask, Gs = scene._sparse["mask"], scene._sparse["G"]
+        torch.cuda.synchronize()
+    for k in dense:
+        assert torch.equal(dense[k], sparse[k]), k
+    n, H, W, Hd = Gd.shape
+    per = (H * W + 63) // 64
+    m = mask.view(n, per)
+    assert set(m.unique().tolist()) <= {0, 2}
+    frac = (m != 0).float().mean().item()
+    assert 0.0 < frac < 0.8, frac
+    tile_of_pixel = (torch.arange(H * W, device="cuda") // 64)
+    folded = (m != 0)[:, tile_of_pixel].view(n, H, W)
+    assert torch.equal(Gs[folded], Gd[folded])                 # same kernel, same operands: identical values
+    print("tiles folded:", frac)
+
+
+def test_sparse_training_step_gradients_equal_the_dense_path():
+    """Autograd through the drop-in classes with the sparse fold (default) and with it switched off: outputs identical,
+    gradients equal up to the order of the atomic accumulation."""
+    from behindthescenes_b200 import synthetic as syn
+    wl = _patch_workload(seed=9)
+    res = {}
+    for mode in (True, False):
+        net, wrapped = syn.build_model(wl, "cuda")
+        net.sparse_fold = mode
+        net.encoder.feats.requires_grad_(True)
+        net.encode(wl.images.cuda(), wl.Ks.cuda(), wl.poses_c2w.cuda(), ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
+        out = wrapped(wl.rays.cuda(), u=wl.u.cuda(), want_weights=True, want_alphas=True)["coarse"]
+        loss = out["depth"].mean() * 0.1 + (out["rgb"] ** 2).mean() + out["weights"].sum(-1).mean() * 0.01
+        loss.backward()
+        torch.cuda.synchronize()
+        grads = {"feats": net.encoder.feats.grad.clone()}
+        grads.update({k: p.grad.clone() for k, p in net.mlp_coarse.named_parameters()})
+        res[mode] = (out["depth"].detach().clone(), out["rgb"].detach().clone(), grads)
+    assert torch.equal(res[True][0], res[False][0]) and torch.equal(res[True][1], res[False][1])
+    for k, gs in res[True][2].items():
+        gd = res[False][2][k]
+        assert torch.isfinite(gs).all(), k
+        err = (gs - gd).abs().max().item() / max(gd.abs().max().item(), 1e-12)
+        assert err <= 2e-5, (k, err)
+    # untouched pixels of the feature gradient are exact zeros in both paths
+    assert (res[True][2]["feats"] == 0).float().mean().item() > 0.1

@@ -157,7 +157,10 @@ def cfg3_train_step(dev, peaks, steps=10, with_reference=True):
     world = _world()
     n, Rr = 16, 2048                      # configs/exp_kitti_raw.yaml:11,59-61: batch 16, ray_batch_size 2048, 8x8 patches
     H, W = 370, 1226                      # KITTI-Raw frame (BASELINE config 3)
-    wl = syn.cfg3_kitti_raw_train(H=H, W=W, n=n, lin_out_bias=-4.0, seed=61, ray_subsample=Rr)
+    wl = syn.cfg3_kitti_raw_train(H=H, W=W, n=n, lin_out_bias=-4.0, seed=61)
+    # the rays of a training batch are 8x8 pixel patches (PatchRaySampler; 2048 rays = 32 patches per frame), drawn
+    # independently per frame from the two loss views
+    wl = syn.with_patch_rays(wl, H, W, 2, Rr // 64, seed=61)
     cpu_net, _ = syn.build_model(wl, "cpu")
     sd = {k: v.clone() for k, v in cpu_net.state_dict().items() if not k.startswith("encoder.")}
     net, wrapped = syn.build_model(wl, dev, state_dict=sd)
@@ -211,7 +214,7 @@ def cfg3_train_step(dev, peaks, steps=10, with_reference=True):
     ms_graph = timed_steps(graph_step, dev, steps, 2) if captured else None
     crit.sync_scalars = True
     ms = min(ms_eager, ms_graph) if ms_graph is not None else ms_eager
-    res = {"what": f"cfg3 KITTI-Raw training step: {n} frames {H}x{W} x {Rr} patch rays per GPU, K=64, 2 render views, fold + render + "
+    res = {"what": f"cfg3 KITTI-Raw training step: {n} frames {H}x{W} x {Rr} rays per GPU in 8x8 patches (PatchRaySampler), K=64, 2 render views, fold + render + "
                    "shipped loss (l1+ssim, weight-guided mask, edge-aware smoothness) + backward (+ gradient all-reduce); encoder excluded",
            "rays_per_gpu": n * Rr, "ms_per_step": ms, "rays_per_s": world * n * Rr / ms * 1e3, "ms_per_step_eager": ms_eager,
            "ms_per_step_cuda_graph": ms_graph, "cuda_graph": captured, "host_enqueue_ms_eager": host_ms, "scaling": "weak"}
@@ -219,10 +222,16 @@ def cfg3_train_step(dev, peaks, steps=10, with_reference=True):
     # zeroed + read, F read, dF written), the render forward / backward do the positional-code contraction per sample
     # (x3: the backward recomputes it and forms two gradient products) and move the per-ray tensors
     px = n * H * W
-    flop = 3 * 2 * 64 * 64 * px + 3 * 64 * (2 * 39 * 64 + 2 * 64) * n * Rr
-    byts = 6 * px * 64 * 4 + n * Rr * (32 + 256 + 24 + 4 + 8 + 3 * 256 + 32 + 256 + 256 + 24 + 4 + 2 * 256)
+    # sparse fold: only the 64-pixel tiles the patches' epipolar lines cross are folded / differentiated; the dense part
+    # that remains is the feature gradient (written once, zeros outside those tiles)
+    hit = net._scene_cache.get(("sparse", 0))
+    frac = float((hit[1]._sparse["mask"] != 0).float().mean().item()) if hit is not None else 1.0
+    res["tiles_sampled_frac"] = frac
+    flop = 3 * 2 * 64 * 64 * px * frac + 3 * 64 * (2 * 39 * 64 + 2 * 64) * n * Rr
+    byts = (1 + 5 * frac) * px * 64 * 4 + n * Rr * (32 + 256 + 24 + 4 + 8 + 3 * 256 + 32 + 256 + 256 + 24 + 4 + 2 * 256)
     res["roofline"] = roofline(1e3 / ms, flop, byts, peaks)       # "rays" = steps here: totals per step
-    res["roofline"]["note"] = "totals per step per GPU (fold fwd+bwd traffic dominates: full-resolution maps for 2048 rays per frame)"
+    res["roofline"]["note"] = ("totals per step per GPU: feature gradient written densely (px x C x 4 B) + 5 map-sized streams over the "
+                               f"sampled tiles ({frac:.2f} of the map: F read twice, G written, d_G zeroed and read) + per-ray tensors")
     if with_reference and world == 1:
         from oracle import bts_oracle as orc
         from oracle import loss_oracle as lo
