@@ -343,6 +343,7 @@ class BTSNet(nn.Module):
         st = scene._sparse
         cfg, keep3 = self._cfg_struct(renderer)
         rays_d = _dev_f32(rays)
+        self._require_cuda(rays_d)         # no CPU fallback
         n, R, _ = rays_d.shape
         dev = rays_d.device
         u_d = _dev_f32(u.to(dev)) if u is not None else None
