@@ -626,6 +626,7 @@ def run_ours(args):
             net.encode(wl.images.to(dev), wl.Ks.to(dev), wl.poses_c2w.to(dev), ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
         wrapped.renderer.precision = args.precision
         frame_dev = frame_rays.to(dev)
+        guarded("frame_with_encoder_standin", lambda: bw.frame_with_encoder(wl, sd, dev, steps=min(args.steps, 10)))
         guarded("strong_cfg2_frame", lambda: bw.strong_cfg2(net, wrapped, frame_dev, dev, min(args.steps, 50), flush))
         del frame_dev
         guarded("cfg3_train_step", lambda: bw.cfg3_train_step(dev, pk, steps=min(args.steps, 10), with_reference=(world == 1 and not args.no_ref_gpu)))

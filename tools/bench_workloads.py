@@ -312,3 +312,69 @@ def cfg4_re10k(dev, peaks, steps=10, with_parity=True):
                          "max_abs_weights": (got["weights"].cpu() - ref["weights"])[same].abs().max().item(),
                          "flag_flip_rays": int((~same).sum().item())}
     return res
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# What a user's frame costs with an encoder in front: encoder stand-in + encode() glue + render through the public API
+# ---------------------------------------------------------------------------------------------------------------------
+
+class _EncoderStandIn(torch.nn.Module):
+    """A stand-in with the SHAPE of the reference's backbone (``models/common/backbones/monodepth2.py``: ResNet-50 trunk,
+    U-Net decoder with skip connections up to full resolution, d_out = 64 feature channels), random weights, written here
+    from torchvision's ResNet -- the encoder itself is out of scope (SURVEY.md §2) and the reference is not on the GPU box;
+    this only prices ``encode()`` so that the render time can be put next to it."""
+
+    def __init__(self, d_out=64):
+        super().__init__()
+        import torchvision
+        r = torchvision.models.resnet50(weights=None)
+        self.stem = torch.nn.Sequential(r.conv1, r.bn1, r.relu)
+        self.pool, self.layers = r.maxpool, torch.nn.ModuleList([r.layer1, r.layer2, r.layer3, r.layer4])
+        enc = [64, 256, 512, 1024, 2048]
+        dec = [max(d_out, c) for c in (16, 32, 64, 128, 256)]
+        conv = lambda i, o: torch.nn.Sequential(torch.nn.ReflectionPad2d(1), torch.nn.Conv2d(i, o, 3), torch.nn.ELU(inplace=True))  # noqa: E731
+        self.up0 = torch.nn.ModuleList([conv(enc[4] if i == 4 else dec[i + 1], dec[i]) for i in range(5)])
+        self.up1 = torch.nn.ModuleList([conv(dec[i] + (enc[i - 1] if i > 0 else 0), dec[i]) for i in range(5)])
+        self.out = torch.nn.Conv2d(dec[0], d_out, 1)
+        self.latent_size, self.scales = d_out, [0]
+
+    def forward(self, x):
+        f = [self.stem(x)]
+        y = self.pool(f[0])
+        for layer in self.layers:
+            y = layer(y)
+            f.append(y)
+        y = f[4]
+        for i in range(4, -1, -1):
+            y = torch.nn.functional.interpolate(self.up0[i](y), scale_factor=2, mode="nearest")
+            if i > 0:
+                y = torch.cat((y, f[i - 1]), 1)
+            y = self.up1[i](y)
+        return [self.out(y)]
+
+
+def frame_with_encoder(wl, sd, dev, steps=10):
+    """encode() (stand-in encoder + the path's glue) + render of the cfg2 stereo frame through the drop-in classes."""
+    net, wrapped = syn.build_model(wl, dev, state_dict=sd)
+    net.encoder = _EncoderStandIn(net.encoder.latent_size).to(dev).eval()
+    imgs, Ks, poses, rays = (t.to(dev) for t in (wl.images, wl.Ks, wl.poses_c2w, wl.rays))
+    wants = dict(want_weights=True, want_alphas=True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    t_enc = t_all = 0.0
+    with torch.no_grad():
+        for i in range(-3, steps):
+            ev[0].record()
+            net.encode(imgs, Ks, poses, ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
+            ev[1].record()
+            wrapped(rays, **wants)
+            ev[2].record()
+            torch.cuda.synchronize(dev)
+            if i >= 0:
+                t_enc += ev[0].elapsed_time(ev[1])
+                t_all += ev[0].elapsed_time(ev[2])
+    n_rays = rays.shape[1]
+    ms_enc, ms_all = _max_over_ranks(t_enc / steps, dev), _max_over_ranks(t_all / steps, dev)
+    return {"what": "cfg2 stereo frame with an encoder in front: net.encode() with a ResNet-50 + U-Net stand-in of the reference backbone's shape "
+                    "(random weights, fp32 eager cuDNN; NOT the reference's encoder, which is out of scope and not on this box) + fold + pack + render",
+            "ms_encode_standin": ms_enc, "ms_fold_pack_render": ms_all - ms_enc, "ms_per_frame": ms_all,
+            "rays_per_s": n_rays * _world() / (ms_all * 1e-3), "render_share": (ms_all - ms_enc) / ms_all}
