@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libbts_b200.so")
+LIB_PATH = os.environ.get("BTS_B200_LIB") or os.path.join(_PKG, "lib", "libbts_b200.so")   # override: kernel experiments
 
 BTS_MAX_BLOCKS = 8
 ABI_VERSION = 11

@@ -43,6 +43,13 @@ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
   h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
   return h;
 }
+// the same generator for ray indices below 2^32, with the seed words pre-mixed once per kernel:
+// seed_lo = (uint32_t)seed, seed_mix = (uint32_t)(seed >> 32) * 0x27D4EB2F
+__device__ __forceinline__ float hash_uniform32(uint32_t seed_lo, uint32_t seed_mix, uint32_t ray, uint32_t k) {
+  uint32_t h = ray * 0x9E3779B1u + k * 0x85EBCA77u + seed_lo;
+  h = fmix32(h ^ seed_mix ^ 0x165667B1u);
+  return (float)(h >> 8) * (1.0f / 16777216.0f);
+}
 __device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t ray, uint32_t k) {
   uint32_t h = (uint32_t)ray * 0x9E3779B1u + k * 0x85EBCA77u + (uint32_t)seed;
   h ^= (uint32_t)(ray >> 32) * 0xC2B2AE3Du + (uint32_t)(seed >> 32) * 0x27D4EB2Fu;

@@ -123,9 +123,19 @@ __device__ __forceinline__ void group_sync(int group) {   // barrier over the 4 
 }
 // F.softplus(beta=1, threshold=20) (models_bts.py:313) = max(x, 0) + log1p(exp(-|x|)): the exponential is <= 1, so
 // ex2 / lg2 on the SFU keep the absolute error at the 1e-7 level (the argument 1 + e is rounded once)
+__device__ __forceinline__ float ex2_sfu(float x) {   // 2^x, x <= 0 here: no overflow; results below 2^-126 flush to 0
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float lg2_sfu(float x) {   // log2(x), x in [1, 2] here
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float softplus_sfu(float x) {
-  const float e = exp2f(-fabsf(x) * 1.44269504088896340736f);
-  return fmaxf(x, 0.0f) + 0.69314718055994530942f * log2f(1.0f + e);
+  const float e = ex2_sfu(-fabsf(x) * 1.44269504088896340736f);
+  return fmaxf(x, 0.0f) + 0.69314718055994530942f * lg2_sfu(1.0f + e);
 }
 
 // Software pipeline of a tile group (tile i = chunk i of the group's 8 rays), one group barrier per tile:
@@ -286,6 +296,7 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
   const size_t copy_bytes = (size_t)H * Wo * Lt::kBlk;     // one copy of G16 (scene.n == 1)
 
   const uint64_t seed_eff = jitter_seed(p);
+  const uint32_t seed_lo = (uint32_t)seed_eff, seed_mix = (uint32_t)(seed_eff >> 32) * 0x27D4EB2Fu;   // hash_uniform32
   const int n_rays = (int)p.n_items;                        // < 2^31 (launcher)
   const int n_pass = (n_rays + 7) / 8;
   const int pass0 = (int)blockIdx.x * kGroups + group, pass_stride = (int)gridDim.x * kGroups;
@@ -342,7 +353,7 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
     // P0 of a chunk: depth (nerf.py:103-123, rounded like the reference's separate elementwise ops), world point,
     // projection into the encoder view, depth code, bilinear taps; the warp's tap footprint is published
     auto stage_p0 = [&](int k, float& z, float& pu, float& pv_, float& pcode) -> Tap {
-      const float uu = p.u ? __ldg(p.u + (int64_t)ray * K + k) : hash_uniform(seed_eff, (uint64_t)ray, (uint32_t)k);
+      const float uu = p.u ? __ldg(p.u + (int64_t)ray * K + k) : hash_uniform32(seed_lo, seed_mix, (uint32_t)ray, (uint32_t)k);
       const float s = __fadd_rn(s_zsteps[k], __fmul_rn(uu, cfg.step));
       const float one_m = __fsub_rn(1.0f, s);
       const float zz = __fadd_rn(__fmul_rn(near_, one_m), __fmul_rn(far_, s));
@@ -586,31 +597,47 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
       // ---------------- P3: accumulator -> sigma ----------------
       const bool inv_f = (tap.bits >> 26) & 1, empty_me = (tap.bits >> 27) & 1, big = (tap.bits >> 28) & 1;
       float logit = b_out;
-      if (!__any_sync(kFull, big || empty_me)) {           // warp-uniform: tcgen05.ld is warp-collective
-        uint64_t l01 = pack2(0.0f, 0.0f), l23 = l01, l45 = l01, l67 = l01;   // 8 chains in 4 packed accumulators
+      const bool any_big = __any_sync(kFull, big), any_empty = __any_sync(kFull, empty_me);   // warp-uniform: tcgen05.ld is warp-collective
+      if (!any_big) {
+        // samples outside the encoder frustum take the learned empty row instead of the band (their weights are zero):
+        // the warp that holds one adds m * g_empty to every accumulator column, m = 1 on those lanes
+        auto fast_logit = [&](auto with_empty) {
+          constexpr bool kE = decltype(with_empty)::value;
+          const uint64_t m2 = pack2(empty_me ? 1.0f : 0.0f, empty_me ? 1.0f : 0.0f);
+          uint64_t l01 = pack2(0.0f, 0.0f), l23 = l01, l45 = l01, l67 = l01;   // 8 chains in 4 packed accumulators
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {                    // 32 accumulator columns at a time (register budget)
-          uint32_t dv[2][16];
-          tc::tmem_ld_x16(t_lane + Lt::kColD + hh * 32, dv[0]);
-          tc::tmem_ld_x16(t_lane + Lt::kColD + hh * 32 + 16, dv[1]);
-          tc::tmem_ld_wait();
-          const float4* wo4 = reinterpret_cast<const float4*>(s_wout) + hh * 8;
+          for (int hh = 0; hh < 2; ++hh) {                    // 32 accumulator columns at a time (register budget)
+            uint32_t dv[2][16];
+            tc::tmem_ld_x16(t_lane + Lt::kColD + hh * 32, dv[0]);
+            tc::tmem_ld_x16(t_lane + Lt::kColD + hh * 32 + 16, dv[1]);
+            tc::tmem_ld_wait();
+            const float4* wo4 = reinterpret_cast<const float4*>(s_wout) + hh * 8;
+            const float4* ge4 = reinterpret_cast<const float4*>(s_gempty) + hh * 8;
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
+            for (int c = 0; c < 2; ++c) {
 #pragma unroll
-            for (int e = 0; e < 4; e += 2) {
-              const float4 wa = wo4[c * 4 + e], wb = wo4[c * 4 + e + 1];
-              ffma2(l01, pack2(fmaxf(__uint_as_float(dv[c][e * 4 + 0]), 0.0f), fmaxf(__uint_as_float(dv[c][e * 4 + 1]), 0.0f)), pack2(wa.x, wa.y));
-              ffma2(l23, pack2(fmaxf(__uint_as_float(dv[c][e * 4 + 2]), 0.0f), fmaxf(__uint_as_float(dv[c][e * 4 + 3]), 0.0f)), pack2(wa.z, wa.w));
-              ffma2(l45, pack2(fmaxf(__uint_as_float(dv[c][e * 4 + 4]), 0.0f), fmaxf(__uint_as_float(dv[c][e * 4 + 5]), 0.0f)), pack2(wb.x, wb.y));
-              ffma2(l67, pack2(fmaxf(__uint_as_float(dv[c][e * 4 + 6]), 0.0f), fmaxf(__uint_as_float(dv[c][e * 4 + 7]), 0.0f)), pack2(wb.z, wb.w));
+              for (int e = 0; e < 4; ++e) {
+                const float4 wa = wo4[c * 4 + e];
+                uint64_t h01 = pack2(__uint_as_float(dv[c][e * 4 + 0]), __uint_as_float(dv[c][e * 4 + 1]));
+                uint64_t h23 = pack2(__uint_as_float(dv[c][e * 4 + 2]), __uint_as_float(dv[c][e * 4 + 3]));
+                if (kE) {
+                  const float4 ga = ge4[c * 4 + e];
+                  ffma2(h01, m2, pack2(ga.x, ga.y));
+                  ffma2(h23, m2, pack2(ga.z, ga.w));
+                }
+                const float2 a = unpack2(h01), bq = unpack2(h23);
+                ffma2((e & 1) ? l45 : l01, pack2(fmaxf(a.x, 0.0f), fmaxf(a.y, 0.0f)), pack2(wa.x, wa.y));
+                ffma2((e & 1) ? l67 : l23, pack2(fmaxf(bq.x, 0.0f), fmaxf(bq.y, 0.0f)), pack2(wa.z, wa.w));
+              }
             }
           }
-        }
-        const float2 s01 = unpack2(l01), s23 = unpack2(l23), s45 = unpack2(l45), s67 = unpack2(l67);
-        const float l0 = s01.x + s45.x, l1 = s01.y + s45.y, l2 = s23.x + s67.x, l3 = s23.y + s67.y;
-        logit += (l0 + l1) + (l2 + l3);
-      } else {   // rare: learned empty row and/or the raw-coordinate part of lin_in added in fp32 (code recomputed)
+          const float2 s01 = unpack2(l01), s23 = unpack2(l23), s45 = unpack2(l45), s67 = unpack2(l67);
+          const float l0 = s01.x + s45.x, l1 = s01.y + s45.y, l2 = s23.x + s67.x, l3 = s23.y + s67.y;
+          logit += (l0 + l1) + (l2 + l3);
+        };
+        if (any_empty) fast_logit(std::true_type{});
+        else fast_logit(std::false_type{});
+      } else {   // rare (a sample far outside the frustum): the raw-coordinate part of lin_in added in fp32 (code recomputed)
         float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f;
         if (big) {
           const Proj pq = project(view_of(0), __fadd_rn(ry.o[0], __fmul_rn(z, ry.d[0])), __fadd_rn(ry.o[1], __fmul_rn(z, ry.d[1])),
@@ -637,7 +664,8 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
 
       // ---------------- C: alpha compositing over the 16 samples of the chunk (nerf.py:283-299) ----------------
       const float delta = (k + 1 < K) ? __fsub_rn(z_next, z) : 1e10f;
-      float alpha = __fsub_rn(1.0f, expf(-(fabsf(delta) * fmaxf(sigma, 0.0f))));
+      // exp(-x), x >= 0, as 2^(-x log2 e) on the SFU: absolute error ~1e-7
+      float alpha = __fsub_rn(1.0f, ex2_sfu(-(fabsf(delta) * fmaxf(sigma, 0.0f)) * 1.44269504088896340736f));
       if (cfg.hard_alpha_cap && k == K - 1) alpha = 1.0f;
       const float tr = active ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;
       float incl = tr;
