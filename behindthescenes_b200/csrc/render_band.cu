@@ -506,25 +506,22 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[v][c] = 0.0f;
     }
-    // ---- prologue: operands of the first tile ----
-    float z, pu, pv_, pcode;
-    Tap tap = stage_p0(hl, z, pu, pv_, pcode);
-    Geom geom = stage_geom();
-    if (geom.nsteps > kTmax) { fail_group(); continue; }
-    issue_band(geom);
-    stage_code(pu, pv_, pcode, (tap.bits >> 28) & 1);
-    Slots slots = stage_scatter(tap, geom);
-    tc::tmem_st_wait();
-    tc::fence_proxy_async_smem();          // weight-operand stores -> async proxy (tensor core)
-    tc::tc_fence_before_sync();
+    // One loop body serves the whole pass: iteration -1 only prepares the operands of the first tile (the "next tile" half of
+    // the body), iterations 0 .. K/16 - 1 consume a tile and prepare the following one -- a single copy of the sampling / code /
+    // scatter code in the instruction stream.
+    float z = 0.0f, pu = 0.0f, pv_ = 0.0f, pcode = 0.0f;
+    Tap tap = {0, 0.0f, 0.0f};
+    Geom geom = {0, 0, 1, 0, 0};
+    Slots slots = {0u, 0u, 0u, 0u};
     bool failed = false;
 
-    for (int c0 = 0; c0 < K; c0 += 16) {
+    for (int c0 = -16; c0 < K; c0 += 16) {
+      const bool cur = c0 >= 0;            // a tile to consume (warp-uniform)
       const int k = c0 + hl;
       const uint32_t sample_id = (uint32_t)ray * (uint32_t)K + (uint32_t)k;   // < 2^31 elements per output (launcher)
-      group_sync(group);                   // operands of this tile complete; the previous tile is fully consumed
+      if (cur) group_sync(group);          // operands of this tile complete; the previous tile is fully consumed
       // ---------------- MMA issue (one thread of the group) ----------------
-      if (__shfl_sync(kFull, warp, 0) == mma_warp) {   // whole warp (uniform operands), one elected lane issues
+      if (cur && __shfl_sync(kFull, warp, 0) == mma_warp) {   // whole warp (uniform operands), one elected lane issues
         const int nsteps_u = __shfl_sync(kFull, geom.nsteps, 0), no_u = __shfl_sync(kFull, geom.no, 0);
         const bool leader = tc::elect_one();
         tc::tc_fence_after_sync();
@@ -559,7 +556,7 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
         }
         if (leader) tc::mma_commit(bar_mma);
       }
-      if (geom.nsteps > 0) tma_phase ^= 1u;
+      if (cur && geom.nsteps > 0) tma_phase ^= 1u;
       __syncwarp();
 
       // ---------------- P0 of the next chunk, while the MMAs run ----------------
@@ -571,16 +568,18 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
       const float z_first_of_next = __shfl_sync(kFull, z_n, 0, 16);
       if (hl == 15) z_next = z_first_of_next;
 
-      tc::mbar_wait_or_trap(bar_mma, mma_phase, &g_band_barrier_timeouts);
-      mma_phase ^= 1u;
-      tc::tc_fence_after_sync();
-      if (!((tap.bits >> 27) & 1)) {       // clear my weights again: the operand tile is all zeros between tiles
-        const __half zero = __float2half_rn(0.0f);
-        *reinterpret_cast<__half*>(aw_row + slots.a11) = zero; *reinterpret_cast<__half*>(aw_row + slots.a10) = zero;
-        *reinterpret_cast<__half*>(aw_row + slots.a01) = zero; *reinterpret_cast<__half*>(aw_row + slots.a00) = zero;
-        if (kExact) {
-          *reinterpret_cast<__half*>(aw_row + Lt::kPlaneA + slots.a11) = zero; *reinterpret_cast<__half*>(aw_row + Lt::kPlaneA + slots.a10) = zero;
-          *reinterpret_cast<__half*>(aw_row + Lt::kPlaneA + slots.a01) = zero; *reinterpret_cast<__half*>(aw_row + Lt::kPlaneA + slots.a00) = zero;
+      if (cur) {
+        tc::mbar_wait_or_trap(bar_mma, mma_phase, &g_band_barrier_timeouts);
+        mma_phase ^= 1u;
+        tc::tc_fence_after_sync();
+        if (!((tap.bits >> 27) & 1)) {       // clear my weights again: the operand tile is all zeros between tiles
+          const __half zero = __float2half_rn(0.0f);
+          *reinterpret_cast<__half*>(aw_row + slots.a11) = zero; *reinterpret_cast<__half*>(aw_row + slots.a10) = zero;
+          *reinterpret_cast<__half*>(aw_row + slots.a01) = zero; *reinterpret_cast<__half*>(aw_row + slots.a00) = zero;
+          if (kExact) {
+            *reinterpret_cast<__half*>(aw_row + Lt::kPlaneA + slots.a11) = zero; *reinterpret_cast<__half*>(aw_row + Lt::kPlaneA + slots.a10) = zero;
+            *reinterpret_cast<__half*>(aw_row + Lt::kPlaneA + slots.a01) = zero; *reinterpret_cast<__half*>(aw_row + Lt::kPlaneA + slots.a00) = zero;
+          }
         }
       }
       // ---------------- operands of the next tile (its band lands during the epilogue below) ----------------
@@ -594,142 +593,144 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
         slots_n = stage_scatter(tap_n, geom_n);
       }
 
-      // ---------------- P3: accumulator -> sigma ----------------
-      const bool inv_f = (tap.bits >> 26) & 1, empty_me = (tap.bits >> 27) & 1, big = (tap.bits >> 28) & 1;
-      float logit = b_out;
-      const bool any_big = __any_sync(kFull, big), any_empty = __any_sync(kFull, empty_me);   // warp-uniform: tcgen05.ld is warp-collective
-      if (!any_big) {
-        // samples outside the encoder frustum take the learned empty row instead of the band (their weights are zero):
-        // the warp that holds one adds m * g_empty to every accumulator column, m = 1 on those lanes
-        auto fast_logit = [&](auto with_empty) {
-          constexpr bool kE = decltype(with_empty)::value;
-          const uint64_t m2 = pack2(empty_me ? 1.0f : 0.0f, empty_me ? 1.0f : 0.0f);
-          uint64_t l01 = pack2(0.0f, 0.0f), l23 = l01, l45 = l01, l67 = l01;   // 8 chains in 4 packed accumulators
+      if (cur) {
+        // ---------------- P3: accumulator -> sigma ----------------
+        const bool inv_f = (tap.bits >> 26) & 1, empty_me = (tap.bits >> 27) & 1, big = (tap.bits >> 28) & 1;
+        float logit = b_out;
+        const bool any_big = __any_sync(kFull, big), any_empty = __any_sync(kFull, empty_me);   // warp-uniform: tcgen05.ld is warp-collective
+        if (!any_big) {
+          // samples outside the encoder frustum take the learned empty row instead of the band (their weights are zero):
+          // the warp that holds one adds m * g_empty to every accumulator column, m = 1 on those lanes
+          auto fast_logit = [&](auto with_empty) {
+            constexpr bool kE = decltype(with_empty)::value;
+            const uint64_t m2 = pack2(empty_me ? 1.0f : 0.0f, empty_me ? 1.0f : 0.0f);
+            uint64_t l01 = pack2(0.0f, 0.0f), l23 = l01, l45 = l01, l67 = l01;   // 8 chains in 4 packed accumulators
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {                    // 32 accumulator columns at a time (register budget)
-            uint32_t dv[2][16];
-            tc::tmem_ld_x16(t_lane + Lt::kColD + hh * 32, dv[0]);
-            tc::tmem_ld_x16(t_lane + Lt::kColD + hh * 32 + 16, dv[1]);
-            tc::tmem_ld_wait();
-            const float4* wo4 = reinterpret_cast<const float4*>(s_wout) + hh * 8;
-            const float4* ge4 = reinterpret_cast<const float4*>(s_gempty) + hh * 8;
+            for (int hh = 0; hh < 2; ++hh) {                    // 32 accumulator columns at a time (register budget)
+              uint32_t dv[2][16];
+              tc::tmem_ld_x16(t_lane + Lt::kColD + hh * 32, dv[0]);
+              tc::tmem_ld_x16(t_lane + Lt::kColD + hh * 32 + 16, dv[1]);
+              tc::tmem_ld_wait();
+              const float4* wo4 = reinterpret_cast<const float4*>(s_wout) + hh * 8;
+              const float4* ge4 = reinterpret_cast<const float4*>(s_gempty) + hh * 8;
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
+              for (int c = 0; c < 2; ++c) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float4 wa = wo4[c * 4 + e];
-                uint64_t h01 = pack2(__uint_as_float(dv[c][e * 4 + 0]), __uint_as_float(dv[c][e * 4 + 1]));
-                uint64_t h23 = pack2(__uint_as_float(dv[c][e * 4 + 2]), __uint_as_float(dv[c][e * 4 + 3]));
-                if (kE) {
-                  const float4 ga = ge4[c * 4 + e];
-                  ffma2(h01, m2, pack2(ga.x, ga.y));
-                  ffma2(h23, m2, pack2(ga.z, ga.w));
+                for (int e = 0; e < 4; ++e) {
+                  const float4 wa = wo4[c * 4 + e];
+                  uint64_t h01 = pack2(__uint_as_float(dv[c][e * 4 + 0]), __uint_as_float(dv[c][e * 4 + 1]));
+                  uint64_t h23 = pack2(__uint_as_float(dv[c][e * 4 + 2]), __uint_as_float(dv[c][e * 4 + 3]));
+                  if (kE) {
+                    const float4 ga = ge4[c * 4 + e];
+                    ffma2(h01, m2, pack2(ga.x, ga.y));
+                    ffma2(h23, m2, pack2(ga.z, ga.w));
+                  }
+                  const float2 a = unpack2(h01), bq = unpack2(h23);
+                  ffma2((e & 1) ? l45 : l01, pack2(fmaxf(a.x, 0.0f), fmaxf(a.y, 0.0f)), pack2(wa.x, wa.y));
+                  ffma2((e & 1) ? l67 : l23, pack2(fmaxf(bq.x, 0.0f), fmaxf(bq.y, 0.0f)), pack2(wa.z, wa.w));
                 }
-                const float2 a = unpack2(h01), bq = unpack2(h23);
-                ffma2((e & 1) ? l45 : l01, pack2(fmaxf(a.x, 0.0f), fmaxf(a.y, 0.0f)), pack2(wa.x, wa.y));
-                ffma2((e & 1) ? l67 : l23, pack2(fmaxf(bq.x, 0.0f), fmaxf(bq.y, 0.0f)), pack2(wa.z, wa.w));
               }
             }
+            const float2 s01 = unpack2(l01), s23 = unpack2(l23), s45 = unpack2(l45), s67 = unpack2(l67);
+            const float l0 = s01.x + s45.x, l1 = s01.y + s45.y, l2 = s23.x + s67.x, l3 = s23.y + s67.y;
+            logit += (l0 + l1) + (l2 + l3);
+          };
+          if (any_empty) fast_logit(std::true_type{});
+          else fast_logit(std::false_type{});
+        } else {   // rare (a sample far outside the frustum): the raw-coordinate part of lin_in added in fp32 (code recomputed)
+          float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f;
+          if (big) {
+            const Proj pq = project(view_of(0), __fadd_rn(ry.o[0], __fmul_rn(z, ry.d[0])), __fadd_rn(ry.o[1], __fmul_rn(z, ry.d[1])),
+                                    __fadd_rn(ry.o[2], __fmul_rn(z, ry.d[2])));
+            r0 = pq.u; r1 = pq.v; r2 = depth_code(cfg, pq);
           }
-          const float2 s01 = unpack2(l01), s23 = unpack2(l23), s45 = unpack2(l45), s67 = unpack2(l67);
-          const float l0 = s01.x + s45.x, l1 = s01.y + s45.y, l2 = s23.x + s67.x, l3 = s23.y + s67.y;
-          logit += (l0 + l1) + (l2 + l3);
-        };
-        if (any_empty) fast_logit(std::true_type{});
-        else fast_logit(std::false_type{});
-      } else {   // rare (a sample far outside the frustum): the raw-coordinate part of lin_in added in fp32 (code recomputed)
-        float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f;
-        if (big) {
-          const Proj pq = project(view_of(0), __fadd_rn(ry.o[0], __fmul_rn(z, ry.d[0])), __fadd_rn(ry.o[1], __fmul_rn(z, ry.d[1])),
-                                  __fadd_rn(ry.o[2], __fmul_rn(z, ry.d[2])));
-          r0 = pq.u; r1 = pq.v; r2 = depth_code(cfg, pq);
-        }
-        const float4* wr4 = reinterpret_cast<const float4*>(smem + Lt::kOffWraw);
+          const float4* wr4 = reinterpret_cast<const float4*>(smem + Lt::kOffWraw);
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t dv[16];
-          tc::tmem_ld_x16(t_lane + Lt::kColD + c * 16, dv);
-          tc::tmem_ld_wait();
+          for (int c = 0; c < 4; ++c) {
+            uint32_t dv[16];
+            tc::tmem_ld_x16(t_lane + Lt::kColD + c * 16, dv);
+            tc::tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const int j = c * 16 + e;
-            const float4 wr = wr4[j];
-            float h = __uint_as_float(dv[e]) + (empty_me ? s_gempty[j] : 0.0f);
-            h = fmaf(wr.z, r2, fmaf(wr.y, r1, fmaf(wr.x, r0, h)));
-            logit = fmaf(fmaxf(h, 0.0f), s_wout[j], logit);
+            for (int e = 0; e < 16; ++e) {
+              const int j = c * 16 + e;
+              const float4 wr = wr4[j];
+              float h = __uint_as_float(dv[e]) + (empty_me ? s_gempty[j] : 0.0f);
+              h = fmaf(wr.z, r2, fmaf(wr.y, r1, fmaf(wr.x, r0, h)));
+              logit = fmaf(fmaxf(h, 0.0f), s_wout[j], logit);
+            }
           }
         }
-      }
-      const float sigma = softplus_sfu(logit);
+        const float sigma = softplus_sfu(logit);
 
-      // ---------------- C: alpha compositing over the 16 samples of the chunk (nerf.py:283-299) ----------------
-      const float delta = (k + 1 < K) ? __fsub_rn(z_next, z) : 1e10f;
-      // exp(-x), x >= 0, as 2^(-x log2 e) on the SFU: absolute error ~1e-7
-      float alpha = __fsub_rn(1.0f, ex2_sfu(-(fabsf(delta) * fmaxf(sigma, 0.0f)) * 1.44269504088896340736f));
-      if (cfg.hard_alpha_cap && k == K - 1) alpha = 1.0f;
-      const float tr = active ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;
-      float incl = tr;
+        // ---------------- C: alpha compositing over the 16 samples of the chunk (nerf.py:283-299) ----------------
+        const float delta = (k + 1 < K) ? __fsub_rn(z_next, z) : 1e10f;
+        // exp(-x), x >= 0, as 2^(-x log2 e) on the SFU: absolute error ~1e-7
+        float alpha = __fsub_rn(1.0f, ex2_sfu(-(fabsf(delta) * fmaxf(sigma, 0.0f)) * 1.44269504088896340736f));
+        if (cfg.hard_alpha_cap && k == K - 1) alpha = 1.0f;
+        const float tr = active ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;
+        float incl = tr;
 #pragma unroll
-      for (int o = 1; o < 16; o <<= 1) {
-        const float up = __shfl_up_sync(kFull, incl, o, 16);
-        if (hl >= o) incl *= up;
-      }
-      float excl = __shfl_up_sync(kFull, incl, 1, 16);
-      if (hl == 0) excl = 1.0f;
-      const float Tk = T_carry * excl;
-      T_carry *= __shfl_sync(kFull, incl, 15, 16);
-      const float wgt = active ? alpha * Tk : 0.0f;
-      depth_part = fmaf(wgt, z, depth_part);
-      wsum_part += wgt;
-      if (active) {
-        if (p.out.weights) p.out.weights[sample_id] = wgt;
-        if (p.out.alphas) p.out.alphas[sample_id] = alpha;
-        if (p.out.z_samps) p.out.z_samps[sample_id] = z;
-        if (p.out.sigma) p.out.sigma[sample_id] = sigma;
-      }
+        for (int o = 1; o < 16; o <<= 1) {
+          const float up = __shfl_up_sync(kFull, incl, o, 16);
+          if (hl >= o) incl *= up;
+        }
+        float excl = __shfl_up_sync(kFull, incl, 1, 16);
+        if (hl == 0) excl = 1.0f;
+        const float Tk = T_carry * excl;
+        T_carry *= __shfl_sync(kFull, incl, 15, 16);
+        const float wgt = active ? alpha * Tk : 0.0f;
+        depth_part = fmaf(wgt, z, depth_part);
+        wsum_part += wgt;
+        if (active) {
+          if (p.out.weights) p.out.weights[sample_id] = wgt;
+          if (p.out.alphas) p.out.alphas[sample_id] = alpha;
+          if (p.out.z_samps) p.out.z_samps[sample_id] = z;
+          if (p.out.sigma) p.out.sigma[sample_id] = sigma;
+        }
 
-      // ---------------- D: colour views (models_bts.py:218-264, :330-334) ----------------
-      if (p.out.rgb || p.out.invalid || p.out.rgb_samps || p.out.invalid_mass) {
-        const int Hc = p.scene.Hc, Wc = p.scene.Wc;
+        // ---------------- D: colour views (models_bts.py:218-264, :330-334) ----------------
+        if (p.out.rgb || p.out.invalid || p.out.rgb_samps || p.out.invalid_mass) {
+          const int Hc = p.scene.Hc, Wc = p.scene.Wc;
 #pragma unroll
-        for (int v = 0; v < VC; ++v) {
-          if (v < Vc) {
-            int x0, y0, dx, dy;
-            float wx1, wy1;
-            bool inv_c;
-            if ((p.scene.same_view_mask >> v) & 1) {   // this colour view is the encoder view: same projection, taps, flags
-              x0 = tap.bits & 0xfff; y0 = (tap.bits >> 12) & 0xfff; dx = (tap.bits >> 24) & 1; dy = (tap.bits >> 25) & 1;
-              wx1 = tap.wx1; wy1 = tap.wy1; inv_c = inv_f;
-            } else {
-              const Proj pc = project(view_of(1 + v), __fadd_rn(ry.o[0], __fmul_rn(z, ry.d[0])), __fadd_rn(ry.o[1], __fmul_rn(z, ry.d[1])),
-                                      __fadd_rn(ry.o[2], __fmul_rn(z, ry.d[2])));
-              const Taps tv = bilinear_taps(pc.u, pc.v, Hc, Wc);
-              x0 = tv.x0; y0 = tv.y0; dx = tv.dx; dy = tv.dy; wx1 = tv.wx1; wy1 = tv.wy1; inv_c = pc.invalid;
-            }
-            float col[4] = {0, 0, 0, 0};
-            if (active) {
-              const float4* base = reinterpret_cast<const float4*>(p.scene.img4) + (uint32_t)((v * Hc + y0) * Wc + x0);
-              const float4 c00 = __ldg(base), c01 = __ldg(base + dx);
-              const float4 c10 = __ldg(base + dy * Wc), c11 = __ldg(base + dy * Wc + dx);
-              const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
-              const float w00 = wx0 * wy0, w01 = wx1 * wy0, w10 = wx0 * wy1, w11 = wx1 * wy1;
-              col[0] = fmaf(c11.x, w11, fmaf(c10.x, w10, fmaf(c01.x, w01, c00.x * w00)));
-              col[1] = fmaf(c11.y, w11, fmaf(c10.y, w10, fmaf(c01.y, w01, c00.y * w00)));
-              col[2] = fmaf(c11.z, w11, fmaf(c10.z, w10, fmaf(c01.z, w01, c00.z * w00)));
-              if (Cc > 3) col[3] = fmaf(c11.w, w11, fmaf(c10.w, w10, fmaf(c01.w, w01, c00.w * w00)));
-            }
-            const float inv = (inv_c | inv_f) ? 1.0f : 0.0f;   // :333-334
-            if (active) {
-              if (p.out.invalid) p.out.invalid[sample_id * (uint32_t)Vc + v] = inv;
-              if (p.out.rgb_samps) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                  if (c < Cc) p.out.rgb_samps[(sample_id * (uint32_t)Vc + v) * (uint32_t)Cc + c] = col[c];
+          for (int v = 0; v < VC; ++v) {
+            if (v < Vc) {
+              int x0, y0, dx, dy;
+              float wx1, wy1;
+              bool inv_c;
+              if ((p.scene.same_view_mask >> v) & 1) {   // this colour view is the encoder view: same projection, taps, flags
+                x0 = tap.bits & 0xfff; y0 = (tap.bits >> 12) & 0xfff; dx = (tap.bits >> 24) & 1; dy = (tap.bits >> 25) & 1;
+                wx1 = tap.wx1; wy1 = tap.wy1; inv_c = inv_f;
+              } else {
+                const Proj pc = project(view_of(1 + v), __fadd_rn(ry.o[0], __fmul_rn(z, ry.d[0])), __fadd_rn(ry.o[1], __fmul_rn(z, ry.d[1])),
+                                        __fadd_rn(ry.o[2], __fmul_rn(z, ry.d[2])));
+                const Taps tv = bilinear_taps(pc.u, pc.v, Hc, Wc);
+                x0 = tv.x0; y0 = tv.y0; dx = tv.dx; dy = tv.dy; wx1 = tv.wx1; wy1 = tv.wy1; inv_c = pc.invalid;
               }
-            }
+              float col[4] = {0, 0, 0, 0};
+              if (active) {
+                const float4* base = reinterpret_cast<const float4*>(p.scene.img4) + (uint32_t)((v * Hc + y0) * Wc + x0);
+                const float4 c00 = __ldg(base), c01 = __ldg(base + dx);
+                const float4 c10 = __ldg(base + dy * Wc), c11 = __ldg(base + dy * Wc + dx);
+                const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
+                const float w00 = wx0 * wy0, w01 = wx1 * wy0, w10 = wx0 * wy1, w11 = wx1 * wy1;
+                col[0] = fmaf(c11.x, w11, fmaf(c10.x, w10, fmaf(c01.x, w01, c00.x * w00)));
+                col[1] = fmaf(c11.y, w11, fmaf(c10.y, w10, fmaf(c01.y, w01, c00.y * w00)));
+                col[2] = fmaf(c11.z, w11, fmaf(c10.z, w10, fmaf(c01.z, w01, c00.z * w00)));
+                if (Cc > 3) col[3] = fmaf(c11.w, w11, fmaf(c10.w, w10, fmaf(c01.w, w01, c00.w * w00)));
+              }
+              const float inv = (inv_c | inv_f) ? 1.0f : 0.0f;   // :333-334
+              if (active) {
+                if (p.out.invalid) p.out.invalid[sample_id * (uint32_t)Vc + v] = inv;
+                if (p.out.rgb_samps) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[v][c] = fmaf(wgt, col[c], acc[v][c]);   // nerf.py:298, reduced once per ray
-            mass[v] = fmaf(wgt, inv, mass[v]);                                      // loss.py:107
+                  for (int c = 0; c < 4; ++c)
+                    if (c < Cc) p.out.rgb_samps[(sample_id * (uint32_t)Vc + v) * (uint32_t)Cc + c] = col[c];
+                }
+              }
+#pragma unroll
+              for (int c = 0; c < 4; ++c) acc[v][c] = fmaf(wgt, col[c], acc[v][c]);   // nerf.py:298, reduced once per ray
+              mass[v] = fmaf(wgt, inv, mass[v]);                                      // loss.py:107
+            }
           }
         }
       }
