@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
     } else {
       ry = fetch_ray(p, ray, lane);       // generated from the pixel's camera (no shuffles on this path)
     }
-    if (g16_bad) {                        // G does not fit fp16: every group goes to the gather kernel
+    if (__builtin_expect(g16_bad, 0)) {   // G does not fit fp16: every group goes to the gather kernel
       if (gt == 0) p.work[4 + atomicAdd(p.work, 1)] = pass;
       continue;
     }
@@ -407,6 +407,7 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
           tc::mbar_expect_tx(bar_tma, row_bytes * (uint32_t)nrows);
           const unsigned char* src = reinterpret_cast<const unsigned char*>(p.scene.G16) + (size_t)(xs_u / 3) * copy_bytes +
                                      ((size_t)yb_u * Wo + ob_u) * Lt::kBlk;
+#pragma unroll 1
           for (int r = 0; r < nrows; ++r)
             tc::bulk_load(s_band + r * row_bytes, src + (size_t)r * Wo * Lt::kBlk, row_bytes, bar_tma);
         }
@@ -414,7 +415,7 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
     };
     // P1a: positional code of (u, v, code) -> A operand in TMEM
     auto stage_code = [&](float pu, float pv_, float pcode, bool big) {
-      if (big) {   // warp-uniform flag (stage_p0): the whole warp evaluates term by term
+      if (__builtin_expect(big, 0)) {   // warp-uniform flag (stage_p0): the whole warp evaluates term by term
         code_far_to_tmem<kExact>(pu, pv_, pcode, cfg.freq_factor, t_lane + Lt::kColAhi, t_lane + Lt::kColAlo);
         return;
       }
@@ -542,6 +543,7 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
             uint64_t a_hi = tc::smem_desc_kmajor_noswizzle(sAw, kChunkA, 128);
             uint64_t b_hi = tc::smem_desc_kmajor_noswizzle(sBand, row_bytes, 128);
             int oct = 0;
+#pragma unroll 1
             for (int ts = 0; ts < nsteps_u; ++ts) {
               tc::mma_f16_ss(tD, a_hi, b_hi, idesc16, 1);
               if (kExact) {
@@ -587,7 +589,7 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
       Slots slots_n = {0u, 0u, 0u, 0u};
       if (has_next) {
         geom_n = stage_geom();
-        if (geom_n.nsteps > kTmax) { failed = true; break; }     // uniform over the group
+        if (__builtin_expect(geom_n.nsteps > kTmax, 0)) { failed = true; break; }     // uniform over the group
         issue_band(geom_n);
         stage_code(pu, pv_, pcode, (tap_n.bits >> 28) & 1);
         slots_n = stage_scatter(tap_n, geom_n);
@@ -598,7 +600,7 @@ __global__ void __launch_bounds__(kThreads, L<HD>::kCtasPerSm) render_band_kerne
         const bool inv_f = (tap.bits >> 26) & 1, empty_me = (tap.bits >> 27) & 1, big = (tap.bits >> 28) & 1;
         float logit = b_out;
         const bool any_big = __any_sync(kFull, big), any_empty = __any_sync(kFull, empty_me);   // warp-uniform: tcgen05.ld is warp-collective
-        if (!any_big) {
+        if (__builtin_expect(!any_big, 1)) {
           // samples outside the encoder frustum take the learned empty row instead of the band (their weights are zero):
           // the warp that holds one adds m * g_empty to every accumulator column, m = 1 on those lanes
           auto fast_logit = [&](auto with_empty) {
