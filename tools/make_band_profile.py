@@ -83,7 +83,7 @@ Commands (under gpurun, one GPU):
 ## Last step of the launch list (cold-cache, serialised: shares, not absolutes)
 ```
 {ll}```
-The render kernel is ~91 % of the step (bench, live CUDA events: 0.92 ms of 1.00 ms); the work-list pass of the gather kernel finds
+The render kernel is ~91 % of the step (bench, live CUDA events: 0.91 ms of 0.99 ms); the work-list pass of the gather kernel finds
 nothing to do on this frame; the per-frame glue (fold, G16 packing of three copies, colour packing) is 6 %.
 
 {summ}
