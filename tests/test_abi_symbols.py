@@ -71,3 +71,16 @@ def test_built_for_sm100a():
     from behindthescenes_b200 import _lib
     out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out, out
+
+
+def test_sparse_fold_entry_points_validate_without_gpu(lib):
+    """The sparse-fold predicate is pure host logic; the entry points reject null pointers before any CUDA call."""
+    assert lib.bts_sparse_fold_supported(64, 192, 640, 64) == 1          # KITTI field: tensor-core fold kernels take it
+    assert lib.bts_sparse_fold_supported(64, 370, 1226, 64) == 1         # full-resolution KITTI-Raw frame (H*W % 4 == 0)
+    assert lib.bts_sparse_fold_supported(48, 16, 16, 64) == 0            # C outside {32, 64}: dense CUDA-core fold only
+    assert lib.bts_sparse_fold_supported(64, 13, 21, 64) == 0            # H*W % 4 != 0
+    assert lib.bts_sparse_fold_supported(64, 192, 640, 128) == 0         # the fold backward kernel stops at d_hidden 64
+    assert lib.bts_mark_tiles(None, None, None, 1, 1, None, 0, None, None) == -1
+    assert lib.bts_fold_features_sparse(None, 1, 64, 4, 4, None, 103, None, 64, None, None, None, None, None) == -1
+    assert lib.bts_zero_tiles(None, 1, 4, 4, 64, None, None) == -1
+    assert lib.bts_fold_features_bwd_sparse(None, None, 1, 64, 4, 4, None, 103, 64, None, None, None, None, None) == -1

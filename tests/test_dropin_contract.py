@@ -178,3 +178,25 @@ def test_reconstruction_loss_constructor_matches_reference_class():
     for cls in (ReconstructionLoss, ref_cls):
         with pytest.raises(ValueError):
             cls({"criterion": "l1+ssim", "alpha_reg_reduction": "patch"})
+
+
+def test_patch_rays_are_pixel_patches_of_the_ray_views():
+    """``synthetic.with_patch_rays`` (the training batches of the bench and the sparse-fold tests): every 64 consecutive rays
+    are one 8x8 pixel window of a ray view, row-major -- the layout ``PatchRaySampler.reconstruct`` views as (n, P, 8, 8)
+    (models/bts/model/ray_sampler.py:189-195) -- and the frames draw different patches."""
+    from behindthescenes_b200 import synthetic as syn
+    H, W, n, P = 40, 96, 3, 5
+    wl = syn.cfg3_kitti_raw_train(H=H, W=W, n=n, seed=3)
+    full = wl.rays.clone().view(n, 2, H, W, 8)
+    wl = syn.with_patch_rays(wl, H, W, 2, P, seed=3)
+    assert wl.rays.shape == (n, P * 64, 8) and wl.u.shape == (n * P * 64, wl.renderer_conf["n_coarse"])
+    flat = full.view(n, 2 * H * W, 8)
+    for b in range(n):
+        for i in range(P):
+            patch = wl.rays[b, i * 64:(i + 1) * 64].view(8, 8, 8)
+            first = (flat[b] == patch[0, 0]).all(-1).nonzero()[0, 0].item()      # (view, y, x) of the patch corner
+            v, rem = divmod(first, H * W)
+            y, x = divmod(rem, W)
+            assert y + 8 <= H and x + 8 <= W
+            assert torch.equal(patch, full[b, v, y:y + 8, x:x + 8])
+    assert not torch.equal(wl.rays[0], wl.rays[1])
