@@ -217,3 +217,59 @@ def test_sparse_training_step_gradients_equal_the_dense_path():
         assert err <= 2e-5, (k, err)
     # untouched pixels of the feature gradient are exact zeros in both paths
     assert (res[True][2]["feats"] == 0).float().mean().item() > 0.1
+
+
+def test_marked_tiles_agree_with_the_oracle_taps():
+    """bts_mark_tiles vs the taps the oracle's sampling + projection + grid_sample arithmetic produce for the same batch
+    (stratified depths nerf.py:103-123, projection models_bts.py:145-155, align_corners=False bilinear taps with border
+    padding): every tile the oracle's taps fall into is marked, and what is marked beyond that is at most the handful of
+    tiles where a tap sits within rounding distance of a pixel boundary."""
+    import ctypes as C
+    from behindthescenes_b200 import synthetic as syn
+    from oracle import bts_oracle as orc
+    H, W = 96, 320
+    wl = _patch_workload(H=H, W=W, n=2, patches=3, seed=11)
+    net, wrapped = syn.build_model(wl, "cuda")
+    lib = _lib.load()
+    with torch.no_grad():
+        net.encode(wl.images.cuda(), wl.Ks.cuda(), wl.poses_c2w.cuda(), ids_encoder=wl.ids_encoder, ids_render=wl.ids_render)
+        scene, keep = net._scene_struct(sparse=True)
+        cfg, keep3 = net._cfg_struct(wrapped.renderer)
+        rays, u = wl.rays.cuda().contiguous(), wl.u.cuda().contiguous()
+        n, R, _ = rays.shape
+        mask = scene._sparse["mask"]
+        rc = lib.bts_mark_tiles(C.byref(scene), C.byref(cfg), rays.data_ptr(), n, R, u.data_ptr(), 0, mask.data_ptr(),
+                                torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "bts_mark_tiles")
+        torch.cuda.synchronize()
+    got = mask.view(n, -1).cpu() != 0
+    # oracle: depths, world points, projection into the encoder view, taps
+    K = wl.renderer_conf["n_coarse"]
+    st = orc.encode_state(wl.images, wl.Ks, wl.poses_c2w, wl.feats, wl.ids_encoder, wl.ids_render)
+    z = orc.stratified_depths(wl.rays.reshape(-1, 8), K, bool(wl.renderer_conf.get("lindisp", True)), wl.u).view(n, R, K)
+    pts = wl.rays[:, :, None, :3] + z.unsqueeze(-1) * wl.rays[:, :, None, 3:6]
+    uv, _, _, _ = orc._project(pts.reshape(n, R * K, 3), st.Kf, st.Mf)
+    uv = uv[:, 0].double()
+    ix = (((uv[..., 0] + 1) * W - 1) / 2).clamp(0, W - 1)
+    iy = (((uv[..., 1] + 1) * H - 1) / 2).clamp(0, H - 1)
+    want = torch.zeros_like(got)
+    near = torch.zeros_like(got)                 # tiles reachable when a tap coordinate is within 1e-3 px of an integer
+    for dx in (0, 1):
+        for dy in (0, 1):
+            x = (ix.floor().long() + dx).clamp(max=W - 1)
+            y = (iy.floor().long() + dy).clamp(max=H - 1)
+            t = (y * W + x) // 64
+            for b in range(n):
+                want[b, t[b]] = True
+    for ex in (-1e-3, 1e-3):
+        for ey in (-1e-3, 1e-3):
+            fx, fy = (ix + ex).clamp(0, W - 1).floor().long(), (iy + ey).clamp(0, H - 1).floor().long()
+            for dx in (0, 1):
+                for dy in (0, 1):
+                    t = ((fy + dy).clamp(max=H - 1) * W + (fx + dx).clamp(max=W - 1)) // 64
+                    for b in range(n):
+                        near[b, t[b]] = True
+    missing = (want & ~got).sum().item()
+    extra = (got & ~want & ~near).sum().item()
+    print("tiles: oracle", int(want.sum()), "marked", int(got.sum()), "oracle-only", missing, "marked-only beyond rounding", extra)
+    assert missing == 0 and extra == 0      # float32 (kernel) vs float64 (here) taps may differ only inside `near`
