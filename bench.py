@@ -563,7 +563,9 @@ def run_ours(args):
                 "config": {"workload": "cfg2 KITTI-360 eval_depth: 192x640 stereo frame, 245760 rays/GPU, K=64, outputs rgb+depth+invalid+weights+alphas",
                            "rays_per_gpu": n_rays, "samples_per_ray": K_SAMPLES, "parallelism": f"ray-shard x{world}",
                            "l2": "256 MiB flush before every timed step", "precision_tier": "exact-fp32" if args.precision == 0 else "fast",
-                           "kernel": kernel_name, "ms_fold_pack": prep_ms, "ms_render": render_ms, "step": "one CUDA-graph launch (6 kernels)" if diag["cuda_graph"] else "eager launches",
+                           "kernel": kernel_name, "ms_fold_pack_eager": prep_ms, "ms_render_eager": render_ms,
+                           "split_note": "fold+pack / render split of the EAGER warm-up steps (events between the launches, host gaps included); the timed step is ms_per_step, the kernel alone roofline.kernel_ms",
+                           "step": "one CUDA-graph launch (6 kernels)" if diag["cuda_graph"] else "eager launches",
                            "ms_metric_tail": metric_tail_ms, "metric": "depth sum + ray count accumulated on a side stream, one NCCL all-reduce at the end",
                            "band_groups_handed_to_gather_kernel": handed, "diag": diag},
                 "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes,
